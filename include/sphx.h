@@ -1,0 +1,258 @@
+/* sphx.h — C ABI of the B200-native SPH-VE hydro step (libsphx.so).
+ *
+ * Drop-in boundary for ONE path of SPH-EXA (sphexa-org/sphexa @ b458f57): the cornerstone neighbour search over the
+ * SFC-sorted octree plus the six SPH-VE particle loops. The reference has no plugin ABI for this path; its seam is the
+ * set of `sph::cuda::computeX` explicit template instantiations in the static library `sph_gpu`
+ * (sph/include/sph/sph_gpu.hpp:24-56, instantiated at hydro_ve/xmass_gpu.cu:131, ve_def_gradh_gpu.cu:99,
+ * iad_divv_curlv_gpu.cu:109, av_switches_gpu.cu:101, momentum_energy_gpu.cu:146-151, eos_gpu.cu:45-75). Every entry point
+ * below names the reference function it replaces. The C++20 wrappers with the reference's own signatures
+ * (sph::computeXMass(const GroupView&, Dataset&, const Box<T>&) ...) live in sphexa_b200/include/sphx/ and only forward
+ * to these functions; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every field pointer is a DEVICE pointer unless the name ends in _host.
+ *  - field types are the reference's production type set (sph/include/sph/types.hpp:39-46, particles_data.hpp:220-248):
+ *    x,y,z,temp,du double; keys uint64; nc unsigned; everything else float.
+ *  - the caller (ParticlesData / Domain in the reference) owns all field and tree memory. The callee reads the pointers
+ *    anew on every call, so buffers may be swapped between calls (field aliasing, ve_hydro.hpp:157-189).
+ *  - outputs are written for particles [first, last) only; halo values of outputs come from the caller's halo exchange.
+ *  - every function returns an int status (SPHX_OK == 0). The reference throws std::runtime_error for the algorithmic
+ *    failures (xmass_gpu.cu:127-128) and exits on CUDA errors (cstone/cuda/errorcheck.cuh:14-26); the C++ wrappers turn the
+ *    status codes back into those behaviours.
+ *  - all work is enqueued on `stream`; functions that return host-visible scalars synchronise that stream.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point returns SPHX_ERR_NO_DEVICE.
+ */
+#ifndef SPHX_H
+#define SPHX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define SPHX_ABI_VERSION 1
+
+    enum SphxStatus
+    {
+        SPHX_OK                 = 0,
+        SPHX_ERR_NO_DEVICE      = 1, /* no CUDA device / driver */
+        SPHX_ERR_CUDA           = 2, /* a CUDA runtime call failed; sphx_last_error() has the text */
+        SPHX_ERR_INVALID        = 3, /* bad argument (null pointer, ng0 > ngmax, ...) */
+        SPHX_ERR_WORKSPACE      = 4, /* workspace too small, see sphx_workspace_bytes */
+        SPHX_ERR_H_CONVERGENCE  = 5, /* coupled h / neighbour-count iteration did not converge (xmass_gpu.cu:128) */
+        SPHX_ERR_NGMAX_OVERFLOW = 6, /* a particle kept more than ngmax neighbours after the h-iteration */
+        SPHX_ERR_TRAVERSAL      = 7, /* traversal stack exhausted (xmass_gpu.cu:127) */
+        SPHX_ERR_NCCL           = 8
+    };
+
+    /* cstone::Box<double> (domain/include/cstone/sfc/box.hpp:94-174). boundary: 0 open, 1 periodic, 2 fixed */
+    typedef struct SphxBox
+    {
+        double lim[6]; /* xmin xmax ymin ymax zmin zmax */
+        int    boundary[3];
+    } SphxBox;
+
+    /* cstone::OctreeNsView<double, uint64_t> (domain/include/cstone/tree/octree.hpp:279-300); device pointers.
+     * Nodes are sorted by (level, SFC key); the 8 children of an internal node are consecutive; childOffsets == 0
+     * marks a leaf; centers/sizes are Vec3<double> (centre, half extent). */
+    typedef struct SphxTreeView
+    {
+        int             numLeafNodes;
+        int             numNodes;
+        const uint64_t* prefixes;       /* numNodes, Warren-Salmon placeholder-bit keys (may be NULL: unused here) */
+        const int*      childOffsets;   /* numNodes */
+        const int*      internalToLeaf; /* numNodes */
+        const int*      levelRange;     /* maxTreeLevel + 2 = 23 (may be NULL: unused here) */
+        const uint64_t* leaves;         /* numLeafNodes + 1 (may be NULL: unused here) */
+        const unsigned* layout;         /* numLeafNodes + 1, index of the first particle of each leaf */
+        const double*   centers;        /* numNodes * 3 */
+        const double*   sizes;          /* numNodes * 3 */
+        float           searchExtFactor;
+    } SphxTreeView;
+
+    /* the fields of sphexa::ParticlesData<GpuTag>::devData this path touches (particles_data.hpp:220-248). Unused /
+     * inactive fields may be NULL (e.g. dV11..dV33 unless avClean). */
+    typedef struct SphxFields
+    {
+        const double* x;
+        const double* y;
+        const double* z;
+        float*        h;  /* in/out of the neighbour search (h-iteration) */
+        const float*  m;
+        const float*  vx;
+        const float*  vy;
+        const float*  vz;
+        const double* temp;
+        const double* u; /* internal energy; used instead of temp when temp == NULL (hydro_ve/eos.hpp:66-91) */
+        unsigned*     nc; /* out: 1 + neighbour count (find_neighbors.hpp:26,36) */
+        float*        xm;
+        float*        kx;
+        float*        gradh;
+        float*        prho;
+        float*        c;
+        float*        rho; /* optional outputs of the EOS */
+        float*        p;
+        float*        c11;
+        float*        c12;
+        float*        c13;
+        float*        c22;
+        float*        c23;
+        float*        c33;
+        float*        divv;
+        float*        curlv;
+        float*        alpha; /* in/out */
+        float*        ax;
+        float*        ay;
+        float*        az;
+        double*       du;
+        float*        dV11; /* avClean only */
+        float*        dV12;
+        float*        dV13;
+        float*        dV22;
+        float*        dV23;
+        float*        dV33;
+    } SphxFields;
+
+    /* scalar attributes of ParticlesData (particles_data.hpp:88-146) */
+    typedef struct SphxParams
+    {
+        double   K;     /* kernel normalisation */
+        double   Kcour; /* Courant factor */
+        double   Krho;  /* 1/|divv| time-step factor */
+        double   gamma;
+        double   minDt; /* current global time step, used by the AV-switch decay */
+        double   polytropic_const;
+        double   polytropic_index;
+        float    muiConst;
+        float    soundSpeedConst;
+        float    alphamin;
+        float    alphamax;
+        float    decay_constant;
+        float    Atmin;
+        float    Atmax;
+        float    ramp;
+        unsigned ng0;
+        unsigned ngmax;
+        int      eosChoice; /* sph::EosType: 0 idealGas, 1 isothermal, 2 polytropic (sph/include/sph/eos.hpp:10-15) */
+        int      avClean;
+    } SphxParams;
+
+    /* cstone::GroupView (domain/include/cstone/traversal/groups.hpp:28-35); device arrays, may be NULL => the callee
+     * uses its own fixed groups of 32 SFC-consecutive particles over [first, last) */
+    typedef struct SphxGroups
+    {
+        unsigned        firstBody, lastBody;
+        unsigned        numGroups;
+        const unsigned* groupStart;
+        const unsigned* groupEnd;
+    } SphxGroups;
+
+    /* Everything one loop needs. */
+    typedef struct SphxStepArgs
+    {
+        SphxFields   f;
+        size_t       numLocal; /* particles incl. halos (array lengths) */
+        size_t       first;    /* first assigned particle (Domain::startIndex) */
+        size_t       last;     /* one past the last assigned particle (Domain::endIndex) */
+        SphxParams   p;
+        SphxBox      box;
+        SphxTreeView tree;
+        const float* wh;  /* 20000-entry kernel table (table_lookup.hpp:10-26), device */
+        const float* whd; /* derivative table, device */
+        void*        workspace; /* device; holds the neighbour list between calls of one step */
+        size_t       workspaceBytes;
+        void*        stream; /* cudaStream_t, NULL = default stream */
+    } SphxStepArgs;
+
+    /* min/max results of the step that the propagator consumes (ts_global.hpp:72-113) */
+    typedef struct SphxStepResult
+    {
+        double        minDtCourant;
+        double        minDtRho;
+        unsigned long totalNeighbors; /* sum of nc over [first,last) (conserved_quantities.hpp:146-157) */
+        unsigned      maxNc;
+        unsigned      numHIterated; /* particles whose h was modified by the iteration */
+    } SphxStepResult;
+
+    const char* sphx_last_error(void);
+    int         sphx_abi_version(void);
+    /* 0 if a usable CUDA device is present, SPHX_ERR_NO_DEVICE otherwise */
+    int sphx_device_check(void);
+
+    /* bytes of workspace for `numAssigned` = last - first particles.
+     * Replaces cstone::allocateNcStacks (traversal/find_neighbors.cuh:492-505). */
+    size_t sphx_workspace_bytes(size_t numAssigned, unsigned ngmax);
+
+    /* host: kernel tables and normalisation constant, sinc^n kernel
+     * (ParticlesData::createTables particles_data.hpp:380-387; sph_kernel_tables.hpp:77-101,144-172) */
+    int sphx_make_tables_host(double sincIndex, float* wh_host, float* whd_host, double* K);
+
+    /* --- the hot path ---------------------------------------------------------------------------------------------- */
+
+    /* Neighbour search with coupled h-iteration, writes h, nc and the neighbour list (into workspace), then xm.
+     * Replaces sph::findNeighborsSfc (sph/find_neighbors.hpp:46-56, a no-op on the reference GPU path) +
+     * sph::cuda::computeXMass (hydro_ve/xmass_gpu.cu:104-129). */
+    int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r);
+
+    /* sph::cuda::computeVeDefGradh (hydro_ve/ve_def_gradh_gpu.cu:50-97): kx, gradh */
+    int sphx_ve_def_gradh(const SphxStepArgs* a);
+    /* sph::computeEOS (hydro_ve/eos.hpp:192-197; eos_gpu.cu:45-160): prho, c (and rho, p when non-NULL) */
+    int sphx_eos(const SphxStepArgs* a);
+    /* sph::cuda::computeIadDivvCurlv (hydro_ve/iad_divv_curlv_gpu.cu:51-107) + sph::rhoTimestep (ts_global.hpp:72-95):
+     * c11..c33, divv, curlv (dV** when avClean), r->minDtRho */
+    int sphx_iad_divv_curlv(const SphxStepArgs* a, SphxStepResult* r);
+    /* sph::cuda::computeAVswitches (hydro_ve/av_switches_gpu.cu:48-99): alpha in/out */
+    int sphx_av_switches(const SphxStepArgs* a);
+    /* sph::cuda::computeMomentumEnergy<avClean> (hydro_ve/momentum_energy_gpu.cu:54-144): ax, ay, az, du, r->minDtCourant */
+    int sphx_momentum_energy(const SphxStepArgs* a, SphxStepResult* r);
+
+    /* halo exchange callback used by sphx_hydro_step between the loops: exchange the `count` listed device arrays
+     * (elemBytes[i] bytes per particle each). Mirrors Domain::exchangeHalos (domain/domain.hpp:372-377). May be NULL. */
+    typedef int (*SphxHaloExchangeFn)(void* user, int count, void* const* arrays, const int* elemBytes);
+
+    /* The whole of HydroVeProp::computeForces after domain sync (main/src/propagator/ve_hydro.hpp:147-190):
+     * search+xmass | halo{xm} | gradh | eos | halo{vx,vy,vz,prho,c,kx} | iad+divv/curlv | halo{c11..c33,divv} |
+     * av switches | halo{alpha} | momentum+energy. The caller provides distinct buffers for gradh/divv/curlv/ay/az or
+     * aliases them exactly as the reference does (ay->gradh, {gradh,az}->{divv,curlv}, {divv,curlv}->{ay,az}). */
+    int sphx_hydro_step(const SphxStepArgs* a, SphxHaloExchangeFn halo, void* haloUser, SphxStepResult* r);
+
+    /* --- cstone call shape ------------------------------------------------------------------------------------------- */
+
+    /* cstone::findNeighbors batch overload (domain/include/cstone/findneighbors.hpp:149-170): for i in [first,last)
+     * neighbors[(i-first)*ngmax + k], counts[i-first] (self excluded, count may exceed ngmax, list truncated).
+     * No h-iteration. List order within a particle is not the reference CPU's DFS order: compare after sorting
+     * (as the reference does for its own GPU search, domain/test/performance/neighbor_driver.cu:255-288). */
+    int sphx_find_neighbors(const double* x, const double* y, const double* z, const float* h, size_t first,
+                            size_t last, const SphxBox* box, const SphxTreeView* tree, unsigned ngmax,
+                            unsigned* neighbors, unsigned* counts, void* stream);
+
+    /* copy the workspace neighbour list of [first,last) into the reference CPU layout neighbors[(i-first)*ngmax + k]
+     * (particles_data.hpp:250-251), e.g. for parity checks. */
+    int sphx_export_neighbors(const SphxStepArgs* a, unsigned* neighbors_dev);
+
+    /* --- callers of the path ("next" rows) ------------------------------------------------------------------------ */
+
+    /* host tree builder: SFC (Hilbert) keys, sort order, cornerstone leaf tree (bucketSize), linked octree, centres.
+     * Replaces for one rank the parts of cstone::Domain::sync that feed OctreeNsView
+     * (domain/domain.hpp:181-234,416-428; sfc/hilbert.hpp:43-93; tree/csarray.hpp:181-430; tree/octree.hpp:78-197). */
+    typedef struct SphxHostTree SphxHostTree;
+    SphxHostTree* sphx_host_tree_build(const double* x_host, const double* y_host, const double* z_host, size_t n,
+                                       const SphxBox* box, unsigned bucketSize);
+    void          sphx_host_tree_free(SphxHostTree*);
+    /* sizes: [0] numNodes, [1] numLeafNodes */
+    void sphx_host_tree_sizes(const SphxHostTree*, int* sizes);
+    /* copy out (host arrays sized by the caller): order[n] (SFC permutation), keys[n] (sorted), and the tree arrays */
+    void sphx_host_tree_get(const SphxHostTree*, unsigned* order, uint64_t* keys, uint64_t* prefixes, int* childOffsets,
+                            int* internalToLeaf, int* levelRange /* 23 */, uint64_t* leaves, unsigned* layout,
+                            double* centers, double* sizes);
+    /* cstone::sfc3D<HilbertKey<uint64_t>> (sfc/sfc.hpp:141-178) for n points */
+    void sphx_hilbert_keys_host(const double* x, const double* y, const double* z, size_t n, const SphxBox* box,
+                                uint64_t* keys);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHX_H */

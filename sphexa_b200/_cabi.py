@@ -1,0 +1,105 @@
+"""ctypes mirror of include/sphx.h. Loads the in-tree libsphx.so; there is no fallback implementation."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libsphx.so"
+
+
+class SphxBox(C.Structure):
+    _fields_ = [("lim", C.c_double * 6), ("boundary", C.c_int * 3)]
+
+
+class SphxTreeView(C.Structure):
+    _fields_ = [("numLeafNodes", C.c_int), ("numNodes", C.c_int), ("prefixes", C.c_void_p),
+                ("childOffsets", C.c_void_p), ("internalToLeaf", C.c_void_p), ("levelRange", C.c_void_p),
+                ("leaves", C.c_void_p), ("layout", C.c_void_p), ("centers", C.c_void_p), ("sizes", C.c_void_p),
+                ("searchExtFactor", C.c_float)]
+
+
+FIELD_NAMES = ("x y z h m vx vy vz temp u nc xm kx gradh prho c rho p c11 c12 c13 c22 c23 c33 divv curlv alpha "
+               "ax ay az du dV11 dV12 dV13 dV22 dV23 dV33").split()
+
+
+class SphxFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in FIELD_NAMES]
+
+
+class SphxParams(C.Structure):
+    _fields_ = [("K", C.c_double), ("Kcour", C.c_double), ("Krho", C.c_double), ("gamma", C.c_double),
+                ("minDt", C.c_double), ("polytropic_const", C.c_double), ("polytropic_index", C.c_double),
+                ("muiConst", C.c_float), ("soundSpeedConst", C.c_float), ("alphamin", C.c_float),
+                ("alphamax", C.c_float), ("decay_constant", C.c_float), ("Atmin", C.c_float), ("Atmax", C.c_float),
+                ("ramp", C.c_float), ("ng0", C.c_uint), ("ngmax", C.c_uint), ("eosChoice", C.c_int),
+                ("avClean", C.c_int)]
+
+
+class SphxStepArgs(C.Structure):
+    _fields_ = [("f", SphxFields), ("numLocal", C.c_size_t), ("first", C.c_size_t), ("last", C.c_size_t),
+                ("p", SphxParams), ("box", SphxBox), ("tree", SphxTreeView), ("wh", C.c_void_p), ("whd", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspaceBytes", C.c_size_t), ("stream", C.c_void_p)]
+
+
+class SphxStepResult(C.Structure):
+    _fields_ = [("minDtCourant", C.c_double), ("minDtRho", C.c_double), ("totalNeighbors", C.c_ulong),
+                ("maxNc", C.c_uint), ("numHIterated", C.c_uint)]
+
+
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
+
+STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ERR_INVALID", 4: "SPHX_ERR_WORKSPACE",
+          5: "SPHX_ERR_H_CONVERGENCE", 6: "SPHX_ERR_NGMAX_OVERFLOW", 7: "SPHX_ERR_TRAVERSAL", 8: "SPHX_ERR_NCCL"}
+
+# every symbol include/sphx.h declares
+EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_workspace_bytes",
+           "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_ve_def_gradh", "sphx_eos",
+           "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
+           "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
+           "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host"]
+
+
+class SphxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libsphx.so. Raises if the library was not built: the product has no Python/CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C sphexa_b200/csrc). There is no fallback implementation.")
+    L = C.CDLL(str(LIB_PATH))
+    L.sphx_last_error.restype = C.c_char_p
+    L.sphx_workspace_bytes.restype = C.c_size_t
+    L.sphx_workspace_bytes.argtypes = [C.c_size_t, C.c_uint]
+    L.sphx_host_tree_build.restype = C.c_void_p
+    L.sphx_host_tree_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint]
+    L.sphx_host_tree_free.argtypes = [C.c_void_p]
+    L.sphx_host_tree_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.sphx_host_tree_get.argtypes = [C.c_void_p] * 11
+    L.sphx_hilbert_keys_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.sphx_make_tables_host.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_find_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                      C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    for name in ("sphx_find_neighbors_xmass", "sphx_iad_divv_curlv", "sphx_momentum_energy"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("sphx_ve_def_gradh", "sphx_eos", "sphx_av_switches"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.sphx_export_neighbors.argtypes = [C.c_void_p, C.c_void_p]
+    L.sphx_hydro_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise SphxError(rc, load().sphx_last_error().decode())

@@ -1,0 +1,389 @@
+/*! @file
+ * Host side of the path's caller ("next" rows of SURVEY §8f): kernel tables, Hilbert keys, SFC order and the
+ * cornerstone octree view the neighbour search consumes — for one rank.
+ *
+ * Replaces (reference paths relative to /root/reference):
+ *   ParticlesData::createTables         sph/include/sph/particles_data.hpp:380-387, sph_kernel_tables.hpp:77-101,144-172
+ *   cstone::sfc3D / iHilbert            domain/include/cstone/sfc/sfc.hpp:141-178, sfc/hilbert.hpp:43-93
+ *   computeOctree (converged)           domain/include/cstone/tree/csarray.hpp:181-430
+ *   buildOctreeCpu / nodeFpCenters      domain/include/cstone/tree/octree.hpp:78-197, focus/source_center.hpp:130-142
+ *
+ * Not a port: the Hilbert curve is a table-driven state machine (orientation state x octant -> digit, next state)
+ * generated at start-up, and the octree is built top-down, one level per pass over the sorted keys, which directly
+ * yields the (level, key)-sorted node layout the reference obtains by sorting Warren-Salmon prefixes. For a converged
+ * tree (every internal node holds more than bucketSize particles, every leaf at most bucketSize) both constructions
+ * give the same arrays, which tests/test_host_tree.py checks against reference dumps.
+ */
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "sphx.h"
+
+namespace
+{
+
+constexpr int      kMaxLevel = 21; // maxTreeLevel<uint64_t>, domain/include/cstone/sfc/common.hpp
+constexpr unsigned kMaxCoord = 1u << kMaxLevel;
+
+/* ------------------------------------------------ Hilbert curve ------------------------------------------------ */
+
+struct Orientation
+{
+    uint8_t perm[3]; // current axis a reads original axis perm[a]
+    uint8_t flip;    // bit (2 - a) set: current axis a is complemented
+    bool    operator==(const Orientation& o) const { return std::memcmp(this, &o, sizeof(Orientation)) == 0; }
+};
+
+struct HilbertTables
+{
+    // indexed [state][octant of ORIGINAL coordinate bits x<<2|y<<1|z]
+    std::vector<std::array<uint8_t, 8>> digit, next;
+    // inverse: [state][digit] -> original octant
+    std::vector<std::array<uint8_t, 8>> octant;
+
+    HilbertTables()
+    {
+        // Per-octant rule of the curve (octant given in CURRENT orientation): Hilbert digit, which axes get
+        // complemented and how axes are permuted for the next finer level.
+        // digit: Morton octant -> Hilbert digit {0,1,3,2,7,6,4,5}
+        const uint8_t m2h[8] = {0, 1, 3, 2, 7, 6, 4, 5};
+        struct Rule
+        {
+            uint8_t flip;    // xyz bits
+            uint8_t perm[3]; // new axis a takes old axis perm[a]
+        } rule[8];
+        for (int o = 0; o < 8; ++o)
+        {
+            int xi = (o >> 2) & 1, yi = (o >> 1) & 1, zi = o & 1;
+            int fx = xi & ((!yi) | zi);
+            int fy = (xi & (yi | zi)) | (yi & (!zi));
+            int fz = (xi & (!yi) & (!zi)) | (yi & (!zi));
+            rule[o].flip = uint8_t(fx << 2 | fy << 1 | fz);
+            if (zi) { rule[o].perm[0] = 1, rule[o].perm[1] = 2, rule[o].perm[2] = 0; } // cyclic rotation
+            else if (!yi) { rule[o].perm[0] = 2, rule[o].perm[1] = 1, rule[o].perm[2] = 0; } // swap x and z
+            else { rule[o].perm[0] = 0, rule[o].perm[1] = 1, rule[o].perm[2] = 2; }
+        }
+
+        std::vector<Orientation> states{Orientation{{0, 1, 2}, 0}};
+        for (size_t s = 0; s < states.size(); ++s)
+        {
+            digit.emplace_back();
+            next.emplace_back();
+            octant.emplace_back();
+            for (int b = 0; b < 8; ++b)
+            {
+                Orientation st = states[s];
+                // current bits = permuted original bits, complemented per axis
+                int cur = 0;
+                for (int a = 0; a < 3; ++a)
+                {
+                    int bit = (b >> (2 - st.perm[a])) & 1;
+                    bit ^= (st.flip >> (2 - a)) & 1;
+                    cur |= bit << (2 - a);
+                }
+                const Rule& r = rule[cur];
+                // new orientation: first complement (flip ^ rule.flip), then permute axes
+                Orientation nx;
+                uint8_t     f = st.flip ^ r.flip;
+                nx.flip       = 0;
+                for (int a = 0; a < 3; ++a)
+                {
+                    nx.perm[a] = st.perm[r.perm[a]];
+                    nx.flip |= ((f >> (2 - r.perm[a])) & 1) << (2 - a);
+                }
+                auto   it  = std::find(states.begin(), states.end(), nx);
+                size_t idx = it - states.begin();
+                if (it == states.end()) { states.push_back(nx); }
+                digit[s][b]           = m2h[cur];
+                next[s][b]            = uint8_t(idx);
+                octant[s][m2h[cur]]   = uint8_t(b);
+            }
+        }
+    }
+};
+
+const HilbertTables& tables()
+{
+    static HilbertTables t;
+    return t;
+}
+
+uint64_t hilbertEncode(unsigned ix, unsigned iy, unsigned iz)
+{
+    const auto& t     = tables();
+    uint64_t    key   = 0;
+    unsigned    state = 0;
+    for (int level = kMaxLevel - 1; level >= 0; --level)
+    {
+        unsigned b = ((ix >> level) & 1u) << 2 | ((iy >> level) & 1u) << 1 | ((iz >> level) & 1u);
+        key        = (key << 3) | t.digit[state][b];
+        state      = t.next[state][b];
+    }
+    return key;
+}
+
+void hilbertDecode(uint64_t key, unsigned& ix, unsigned& iy, unsigned& iz)
+{
+    const auto& t     = tables();
+    unsigned    state = 0;
+    ix = iy = iz = 0;
+    for (int level = kMaxLevel - 1; level >= 0; --level)
+    {
+        unsigned d = unsigned(key >> (3 * level)) & 7u;
+        unsigned b = t.octant[state][d];
+        ix |= ((b >> 2) & 1u) << level;
+        iy |= ((b >> 1) & 1u) << level;
+        iz |= (b & 1u) << level;
+        state = t.next[state][b];
+    }
+}
+
+struct HBox
+{
+    double xmin, ymin, zmin, lx, ly, lz, ilx, ily, ilz;
+    explicit HBox(const SphxBox& b)
+    {
+        xmin = b.lim[0], ymin = b.lim[2], zmin = b.lim[4];
+        lx = b.lim[1] - b.lim[0], ly = b.lim[3] - b.lim[2], lz = b.lim[5] - b.lim[4];
+        ilx = 1.0 / (b.lim[1] - b.lim[0]), ily = 1.0 / (b.lim[3] - b.lim[2]), ilz = 1.0 / (b.lim[5] - b.lim[4]);
+    }
+};
+
+//! normalised integer coordinate as in sfc3D (sfc/sfc.hpp:141-159): floor(x * m) - xmin * m, clipped to 2^21 - 1
+inline unsigned gridCoord(double v, double vmin, double m)
+{
+    int i = int(std::floor(v * m) - vmin * m);
+    return unsigned(std::min(i, int(kMaxCoord - 1)));
+}
+
+void computeKeys(const double* x, const double* y, const double* z, size_t n, const SphxBox& sb, uint64_t* keys)
+{
+    HBox   box(sb);
+    double mx = kMaxCoord * box.ilx, my = kMaxCoord * box.ily, mz = kMaxCoord * box.ilz;
+    tables();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i)
+    {
+        keys[i] = hilbertEncode(gridCoord(x[i], box.xmin, mx), gridCoord(y[i], box.ymin, my),
+                                gridCoord(z[i], box.zmin, mz));
+    }
+}
+
+} // namespace
+
+struct SphxHostTree
+{
+    std::vector<unsigned> order;
+    std::vector<uint64_t> keys;
+    std::vector<uint64_t> prefixes;
+    std::vector<int>      childOffsets, internalToLeaf;
+    std::vector<int>      levelRange;
+    std::vector<uint64_t> leaves;
+    std::vector<unsigned> layout;
+    std::vector<double>   centers, sizes;
+    int                   numNodes{0}, numLeaves{0};
+};
+
+extern "C"
+{
+
+void sphx_hilbert_keys_host(const double* x, const double* y, const double* z, size_t n, const SphxBox* box,
+                            uint64_t* keys)
+{
+    computeKeys(x, y, z, n, *box, keys);
+}
+
+SphxHostTree* sphx_host_tree_build(const double* x, const double* y, const double* z, size_t n, const SphxBox* sbox,
+                                   unsigned bucketSize)
+{
+    auto* t = new SphxHostTree;
+    std::vector<uint64_t> rawKeys(n);
+    computeKeys(x, y, z, n, *sbox, rawKeys.data());
+
+    t->order.resize(n);
+    std::iota(t->order.begin(), t->order.end(), 0u);
+    std::stable_sort(t->order.begin(), t->order.end(), [&](unsigned a, unsigned b) { return rawKeys[a] < rawKeys[b]; });
+    t->keys.resize(n);
+    for (size_t i = 0; i < n; ++i)
+        t->keys[i] = rawKeys[t->order[i]];
+    const std::vector<uint64_t>& keys = t->keys;
+
+    // top-down, level by level. A node is the key range [start, start + 8^(21-level)); it is split while it holds
+    // more than bucketSize particles (the fixed point of the reference's rebalance, csarray.hpp:181-260).
+    struct Node
+    {
+        uint64_t start;
+        unsigned pBegin, pEnd;
+    };
+    std::vector<Node>     level{Node{0, 0u, unsigned(n)}};
+    std::vector<Node>     nodes;
+    std::vector<int>      nodeLevel;
+    t->levelRange.assign(kMaxLevel + 2, 0);
+
+    for (int l = 0; l <= kMaxLevel; ++l)
+    {
+        t->levelRange[l]  = int(nodes.size());
+        size_t levelBegin = nodes.size();
+        nodes.insert(nodes.end(), level.begin(), level.end());
+        nodeLevel.insert(nodeLevel.end(), level.size(), l);
+        t->childOffsets.resize(nodes.size(), 0);
+
+        std::vector<Node> nextLevel;
+        if (l < kMaxLevel)
+        {
+            uint64_t childRange = uint64_t(1) << (3 * (kMaxLevel - l - 1));
+            for (size_t k = 0; k < level.size(); ++k)
+            {
+                const Node& nd = level[k];
+                if (nd.pEnd - nd.pBegin <= bucketSize) continue;
+                // children index: first node of the next level is at nodes.size() + nextLevel.size()
+                t->childOffsets[levelBegin + k] = int(nodes.size() + nextLevel.size());
+                unsigned p                      = nd.pBegin;
+                for (int c = 0; c < 8; ++c)
+                {
+                    uint64_t cs  = nd.start + uint64_t(c) * childRange;
+                    uint64_t ce  = cs + childRange; // may wrap to 2^63 for the last node: compare with care
+                    unsigned end = (c == 7) ? nd.pEnd
+                                            : unsigned(std::lower_bound(keys.begin() + p, keys.begin() + nd.pEnd, ce) -
+                                                       keys.begin());
+                    nextLevel.push_back(Node{cs, p, end});
+                    p = end;
+                }
+            }
+        }
+        level.swap(nextLevel);
+        if (level.empty())
+        {
+            for (int ll = l + 1; ll <= kMaxLevel + 1; ++ll)
+                t->levelRange[ll] = int(nodes.size());
+            break;
+        }
+    }
+    t->levelRange[kMaxLevel + 1] = int(nodes.size());
+    t->numNodes                  = int(nodes.size());
+
+    // leaves in SFC order
+    std::vector<int> leafNodes;
+    for (int i = 0; i < t->numNodes; ++i)
+        if (t->childOffsets[i] == 0) leafNodes.push_back(i);
+    std::sort(leafNodes.begin(), leafNodes.end(), [&](int a, int b) { return nodes[a].start < nodes[b].start; });
+    t->numLeaves = int(leafNodes.size());
+
+    t->internalToLeaf.assign(t->numNodes, -1);
+    t->leaves.resize(t->numLeaves + 1);
+    t->layout.resize(t->numLeaves + 1);
+    for (int k = 0; k < t->numLeaves; ++k)
+    {
+        int nd                 = leafNodes[k];
+        t->internalToLeaf[nd]  = k;
+        t->leaves[k]           = nodes[nd].start;
+        t->layout[k]           = nodes[nd].pBegin;
+    }
+    t->leaves[t->numLeaves] = uint64_t(1) << (3 * kMaxLevel);
+    t->layout[t->numLeaves] = unsigned(n);
+
+    // Warren-Salmon prefixes and geometric centres / half-sizes (sfc/box.hpp:318-334 centerAndSize)
+    t->prefixes.resize(t->numNodes);
+    t->centers.resize(size_t(t->numNodes) * 3);
+    t->sizes.resize(size_t(t->numNodes) * 3);
+    HBox         box(*sbox);
+    const double uL = 1.0 / kMaxCoord;
+    const double hx = 0.5 * uL * box.lx, hy = 0.5 * uL * box.ly, hz = 0.5 * uL * box.lz;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < t->numNodes; ++i)
+    {
+        int l          = nodeLevel[i];
+        t->prefixes[i] = (uint64_t(1) << (3 * l)) | (nodes[i].start >> (3 * (kMaxLevel - l)));
+        unsigned ix, iy, iz;
+        hilbertDecode(nodes[i].start, ix, iy, iz);
+        unsigned cube = kMaxCoord >> l;
+        unsigned mask = ~(cube - 1);
+        ix &= mask, iy &= mask, iz &= mask;
+        int ixmax = int(ix + cube), iymax = int(iy + cube), izmax = int(iz + cube);
+        t->centers[3 * i + 0] = box.xmin + (ixmax + int(ix)) * hx;
+        t->centers[3 * i + 1] = box.ymin + (iymax + int(iy)) * hy;
+        t->centers[3 * i + 2] = box.zmin + (izmax + int(iz)) * hz;
+        t->sizes[3 * i + 0]   = (ixmax - int(ix)) * hx;
+        t->sizes[3 * i + 1]   = (iymax - int(iy)) * hy;
+        t->sizes[3 * i + 2]   = (izmax - int(iz)) * hz;
+    }
+    return t;
+}
+
+void sphx_host_tree_free(SphxHostTree* t) { delete t; }
+
+void sphx_host_tree_sizes(const SphxHostTree* t, int* sizes)
+{
+    sizes[0] = t->numNodes;
+    sizes[1] = t->numLeaves;
+}
+
+void sphx_host_tree_get(const SphxHostTree* t, unsigned* order, uint64_t* keys, uint64_t* prefixes, int* childOffsets,
+                        int* internalToLeaf, int* levelRange, uint64_t* leaves, unsigned* layout, double* centers,
+                        double* sizes)
+{
+    auto cp = [](auto* dst, const auto& v)
+    {
+        if (dst) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    cp(order, t->order), cp(keys, t->keys), cp(prefixes, t->prefixes), cp(childOffsets, t->childOffsets);
+    cp(internalToLeaf, t->internalToLeaf), cp(levelRange, t->levelRange), cp(leaves, t->leaves), cp(layout, t->layout);
+    cp(centers, t->centers), cp(sizes, t->sizes);
+}
+
+/* -------------------------------------------- kernel tables -------------------------------------------- */
+
+int sphx_make_tables_host(double sincIndex, float* wh, float* whd, double* K)
+{
+    if (!wh || !whd || !K) return SPHX_ERR_INVALID;
+    const double halfPi = 1.57079632679489661923; // M_PI_2
+    const double pi     = 3.14159265358979323846;
+    auto sinc = [=](double v)
+    {
+        if (v == 0.0) return 1.0;
+        double pv = halfPi * v;
+        return std::sin(pv) / pv;
+    };
+    auto kernel = [=](double v) { return std::pow(sinc(v), sincIndex); };
+    auto kernelDerivative = [=](double v)
+    {
+        if (v == 0.0) return sincIndex * std::pow(sinc(v), sincIndex - 1) * 0.0;
+        double pv = halfPi * v;
+        double sv = std::sin(pv) / (pv);
+        double ds = sv * halfPi * ((std::cos(pv) / std::sin(pv)) - 1.0 / pv);
+        return sincIndex * std::pow(sinc(v), sincIndex - 1) * ds;
+    };
+
+    // normalisation: 1 / integral of 4 pi x^2 W(x) over [0, 2], composite Simpson with 2000 intervals where odd and
+    // even interior samples are sorted before summation (sph_kernel_tables.hpp:22-56,77-84)
+    {
+        const uint64_t      nInt = 2000;
+        const double        step = 2.0 / double(nInt);
+        auto                vol  = [&](double xx) { return 4.0 * pi * xx * xx * kernel(xx); };
+        std::vector<double> odd, even;
+        for (uint64_t i = 1; i < nInt; ++i)
+            ((i & 1) ? odd : even).push_back(vol(0.0 + double(i) * step));
+        std::sort(odd.begin(), odd.end());
+        std::sort(even.begin(), even.end());
+        double so = std::accumulate(odd.begin(), odd.end(), 0.0), se = std::accumulate(even.begin(), even.end(), 0.0);
+        *K        = 1.0 / (step / 3.0 * (vol(0.0) + vol(2.0) + 4.0 * so + 2.0 * se));
+    }
+
+    // tabulation: the abscissa is stepped and rounded in float, the functor evaluates in double
+    // (sph_kernel_tables.hpp:86-101)
+    const float dx = float((2.0 - 0.0) / 19999);
+    for (size_t i = 0; i < 20000; ++i)
+    {
+        float v = float(0.0 + double(float(i) * dx));
+        wh[i]   = float(kernel(double(v)));
+        whd[i]  = float(kernelDerivative(double(v)));
+    }
+    return SPHX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,216 @@
+"""Python plumbing around the C ABI: torch tensors as device memory for the ParticlesData fields, one call per loop.
+
+Mirrors the field names of sphexa::ParticlesData (sph/include/sph/particles_data.hpp:220-248) and the call order of
+HydroVeProp::computeForces (main/src/propagator/ve_hydro.hpp:130-204). Nothing here computes: every number comes
+out of libsphx.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi, host
+
+F64_FIELDS = ("x", "y", "z", "temp", "du")
+U32_FIELDS = ("nc",)
+STEP_OUTPUTS = ("h", "nc", "xm", "kx", "gradh", "prho", "c", "c11", "c12", "c13", "c22", "c23", "c33", "divv", "curlv",
+                "alpha", "ax", "ay", "az", "du")
+
+
+@dataclass
+class Params:
+    """scalar attributes of ParticlesData with the reference defaults (particles_data.hpp:88-146)"""
+    K: float = 0.0
+    Kcour: float = 0.2
+    Krho: float = 0.06
+    gamma: float = 5.0 / 3.0
+    minDt: float = 1e-12
+    minDt_m1: float = 1e-12
+    polytropic_const: float = 1.0
+    polytropic_index: float = 5.0 / 3.0
+    muiConst: float = 10.0
+    soundSpeedConst: float = 1.0
+    alphamin: float = 0.05
+    alphamax: float = 1.0
+    decay_constant: float = 0.2
+    Atmin: float = 0.1
+    Atmax: float = 0.2
+    ramp: float = 10.0
+    ng0: int = 100
+    ngmax: int = 150
+    eosChoice: int = 0
+    avClean: int = 0
+    maxDtIncrease: float = 1.1
+    ttot: float = 0.0
+
+    @staticmethod
+    def from_dump(d: dict) -> "Params":
+        v = d["params"]
+        return Params(K=v[0], Kcour=v[1], Krho=v[2], gamma=v[3], muiConst=v[4], minDt=v[5], minDt_m1=v[6],
+                      alphamin=v[7], alphamax=v[8], decay_constant=v[9], Atmin=v[10], Atmax=v[11], ramp=v[12],
+                      ttot=v[13], eosChoice=int(v[14]), maxDtIncrease=v[15], ng0=int(d["ng0"][0]),
+                      ngmax=int(d["ngmax"][0]))
+
+    def to_c(self) -> _cabi.SphxParams:
+        p = _cabi.SphxParams()
+        for name, _ in _cabi.SphxParams._fields_:
+            setattr(p, name, getattr(self, name))
+        return p
+
+
+class DeviceTree:
+    """OctreeNsView arrays on the device"""
+
+    def __init__(self, t: host.HostTree | dict, device):
+        if isinstance(t, host.HostTree):
+            t = t.as_dump_dict()
+        self.num_leaves = int(t["numLeafNodes"][0])
+        self.num_nodes = int(t["numNodes"][0])
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(device)  # noqa: E731
+        self.prefixes = up(t["tree_prefixes"], np.int64)
+        self.childOffsets = up(t["tree_childOffsets"], np.int32)
+        self.internalToLeaf = up(t["tree_internalToLeaf"], np.int32)
+        self.levelRange = up(t["tree_levelRange"], np.int32)
+        self.leaves = up(t["tree_leaves"], np.int64)
+        self.layout = up(t["tree_layout"], np.int32)
+        self.centers = up(t["tree_centers"], np.float64)
+        self.sizes = up(t["tree_sizes"], np.float64)
+
+    def view(self) -> _cabi.SphxTreeView:
+        v = _cabi.SphxTreeView()
+        v.numLeafNodes, v.numNodes = self.num_leaves, self.num_nodes
+        for k in ("prefixes", "childOffsets", "internalToLeaf", "levelRange", "leaves", "layout", "centers", "sizes"):
+            setattr(v, k, getattr(self, k).data_ptr())
+        v.searchExtFactor = 1.0
+        return v
+
+
+class HydroData:
+    """Device-resident particle fields + tree + tables + workspace for one rank."""
+
+    def __init__(self, n_local: int, first: int, last: int, box_lim, boundary, params: Params, device="cuda:0",
+                 stream: torch.cuda.Stream | None = None):
+        self.L = _cabi.load()
+        _cabi.check(self.L.sphx_device_check())
+        self.device = torch.device(device)
+        self.n, self.first, self.last = n_local, first, last
+        self.box_lim, self.boundary = [float(v) for v in box_lim], [int(b) for b in boundary]
+        self.p = params
+        self.f: dict[str, torch.Tensor] = {}
+        for name in _cabi.FIELD_NAMES:
+            if name in ("u", "rho", "p") or name.startswith("dV"):
+                continue
+            dt = torch.float64 if name in F64_FIELDS else (torch.int32 if name in U32_FIELDS else torch.float32)
+            self.f[name] = torch.zeros(n_local, dtype=dt, device=self.device)
+        wh, whd, K = host.make_tables()
+        if self.p.K == 0.0:
+            self.p.K = K
+        self.wh = torch.from_numpy(wh).to(self.device)
+        self.whd = torch.from_numpy(whd).to(self.device)
+        self.tree: DeviceTree | None = None
+        nbytes = self.L.sphx_workspace_bytes(last - first, self.p.ngmax)
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.stream = stream
+        self.result = _cabi.SphxStepResult()
+
+    # -- plumbing ---------------------------------------------------------------------------------------------------
+    def set_fields(self, **arrays):
+        for k, a in arrays.items():
+            t = self.f[k]
+            src = torch.from_numpy(np.ascontiguousarray(a).view(np.int32) if t.dtype == torch.int32 else
+                                   np.ascontiguousarray(a))
+            t.copy_(src.to(t.dtype), non_blocking=False)
+
+    def get(self, name) -> np.ndarray:
+        a = self.f[name].cpu().numpy()
+        return a.view(np.uint32) if name in U32_FIELDS else a
+
+    def set_tree(self, t):
+        self.tree = t if isinstance(t, DeviceTree) else DeviceTree(t, self.device)
+
+    def args(self) -> _cabi.SphxStepArgs:
+        a = _cabi.SphxStepArgs()
+        for name in _cabi.FIELD_NAMES:
+            setattr(a.f, name, self.f[name].data_ptr() if name in self.f else None)
+        a.numLocal, a.first, a.last = self.n, self.first, self.last
+        a.p = self.p.to_c()
+        a.box = host.make_box(self.box_lim, self.boundary)
+        a.tree = self.tree.view()
+        a.wh, a.whd = self.wh.data_ptr(), self.whd.data_ptr()
+        a.workspace, a.workspaceBytes = self.workspace.data_ptr(), self.workspace.numel()
+        a.stream = self.stream.cuda_stream if self.stream is not None else None
+        return a
+
+    # -- the six loops, one C-ABI call each --------------------------------------------------------------------------
+    def find_neighbors_xmass(self, sync=True):
+        a = self.args()
+        _cabi.check(self.L.sphx_find_neighbors_xmass(C.byref(a), C.byref(self.result) if sync else None))
+
+    def ve_def_gradh(self):
+        a = self.args()
+        _cabi.check(self.L.sphx_ve_def_gradh(C.byref(a)))
+
+    def eos(self):
+        a = self.args()
+        _cabi.check(self.L.sphx_eos(C.byref(a)))
+
+    def iad_divv_curlv(self, sync=True):
+        a = self.args()
+        _cabi.check(self.L.sphx_iad_divv_curlv(C.byref(a), C.byref(self.result) if sync else None))
+
+    def av_switches(self):
+        a = self.args()
+        _cabi.check(self.L.sphx_av_switches(C.byref(a)))
+
+    def momentum_energy(self, sync=True):
+        a = self.args()
+        _cabi.check(self.L.sphx_momentum_energy(C.byref(a), C.byref(self.result) if sync else None))
+
+    def hydro_step(self, halo=None, sync=True):
+        """sphx_hydro_step: all loops in the reference order; `halo` is an optional Python callable
+        (list[(ptr, elem_bytes)]) -> int used as the halo-exchange callback."""
+        a = self.args()
+        cb = None
+        if halo is not None:
+            def _tramp(user, count, arrays, elem_bytes):
+                return int(halo([(arrays[i], elem_bytes[i]) for i in range(count)]) or 0)
+            cb = _cabi.HALO_FN(_tramp)
+        _cabi.check(self.L.sphx_hydro_step(C.byref(a), cb, None, C.byref(self.result) if sync else None))
+        return self.result
+
+    def export_neighbors(self) -> np.ndarray:
+        out = torch.zeros((self.last - self.first) * self.p.ngmax, dtype=torch.int32, device=self.device)
+        a = self.args()
+        _cabi.check(self.L.sphx_export_neighbors(C.byref(a), C.c_void_p(out.data_ptr())))
+        torch.cuda.synchronize(self.device)
+        return out.cpu().numpy().view(np.uint32)
+
+
+def from_dump(d: dict, device="cuda:0") -> HydroData:
+    """HydroData holding the inputs of one reference-harness dump (single rank: no halos)."""
+    n = int(d["n"][0])
+    hd = HydroData(n, 0, n, d["box"], d["boundary"], Params.from_dump(d), device=device)
+    hd.set_fields(x=d["x"], y=d["y"], z=d["z"], h=d["h_in"], m=d["m"], vx=d["vx"], vy=d["vy"], vz=d["vz"],
+                  temp=d["temp"], alpha=d["alpha_in"])
+    hd.set_tree(d)
+    return hd
+
+
+def find_neighbors(x, y, z, h, tree: DeviceTree, box_lim, boundary, ngmax: int, first=0, last=None, device="cuda:0"):
+    """cstone::findNeighbors call shape through sphx_find_neighbors: returns (neighbors[n*ngmax], counts[n])"""
+    L = _cabi.load()
+    dev = torch.device(device)
+    xd, yd, zd = (torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(dev) for a in (x, y, z))
+    hd = torch.from_numpy(np.ascontiguousarray(h, np.float32)).to(dev)
+    last = xd.numel() if last is None else last
+    n = last - first
+    nb = torch.zeros(max(n * ngmax, 1), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    box = host.make_box(box_lim, boundary)
+    tv = tree.view()
+    _cabi.check(L.sphx_find_neighbors(xd.data_ptr(), yd.data_ptr(), zd.data_ptr(), hd.data_ptr(), first, last,
+                                      C.byref(box), C.byref(tv), ngmax, nb.data_ptr(), cnt.data_ptr(), None))
+    return nb.cpu().numpy().view(np.uint32)[: n * ngmax], cnt.cpu().numpy().view(np.uint32)[:n]

@@ -1,0 +1,198 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI (libsphx.so) against
+(1) golden fixtures produced by the unmodified reference, (2) the CPU restatement (oracle/), (3) the compiled
+reference itself (oracle/_ref/ref_harness) on larger cases, and (4) size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): neighbour counts and sorted neighbour sets bit-exact; fp32 fields <= 1e-4
+relative (measured against the field's max-norm floor, SURVEY §8c: |a-b| <= 1e-4 max(|a|,|b|,floor)).
+"""
+import numpy as np
+import pytest
+
+from refdata import csr_sorted_neighbors, have_ref_harness, load_golden, run_ref_harness
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_F32 = 1e-4
+F32_FIELDS = ["xm", "kx", "gradh", "prho", "c", "c11", "c12", "c13", "c22", "c23", "c33", "divv", "curlv", "alpha",
+              "ax", "ay", "az", "du"]
+STEP_FILES = ["sedov12_step0.npz", "sedov12_step2.npz", "noh14_step0.npz", "turb12_step0.npz", "turb12h_step0.npz"]
+
+
+@pytest.fixture(scope="module")
+def sx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device: the product has no CPU fallback")
+    import sphexa_b200
+    sphexa_b200.load()
+    return sphexa_b200
+
+
+def assert_fields_close(got: dict, ref: dict, fields=F32_FIELDS, tol=REL_TOL_F32):
+    for k in fields:
+        a, b = got[k].astype(np.float64), ref[k].astype(np.float64)
+        # floor: 1e-3 of the field's max magnitude (fields like divv/ax vanish on a lattice at rest)
+        floor = max(np.abs(b).max(), 1e-300) * 1e-3
+        denom = np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+        err = np.abs(a - b) / denom
+        assert err.max() <= tol, f"{k}: max rel err {err.max():.3e} at {err.argmax()} ({a[err.argmax()]} vs {b[err.argmax()]})"
+
+
+def run_step_by_loops(sx, d):
+    """one C-ABI call per loop, in the reference order (ve_hydro.hpp:147-190)"""
+    hd = sx.sim.from_dump(d)
+    hd.find_neighbors_xmass()
+    nb = hd.export_neighbors()
+    hd.ve_def_gradh()
+    hd.eos()
+    hd.iad_divv_curlv()
+    hd.av_switches()
+    hd.momentum_energy()
+    out = {k: hd.get(k) for k in sx.sim.STEP_OUTPUTS}
+    out["neighbors"] = nb
+    out["dts"] = np.array([hd.result.minDtCourant, hd.result.minDtRho])
+    out["totalNeighbors"] = hd.result.totalNeighbors
+    return out, hd
+
+
+def check_against_reference(got, ref):
+    ngmax = int(ref["ngmax"][0])
+    np.testing.assert_array_equal(got["h"], ref["h"])        # h-iteration trajectory bit-exact
+    np.testing.assert_array_equal(got["nc"], ref["nc"])      # neighbour counts bit-exact
+    off, idx = csr_sorted_neighbors(got["neighbors"], got["nc"], ngmax)
+    np.testing.assert_array_equal(off, ref["nb_offsets"])
+    np.testing.assert_array_equal(idx, ref["nb_sorted"])     # sorted neighbour sets bit-exact
+    assert_fields_close(got, ref)
+    np.testing.assert_allclose(got["dts"], ref["dts"], rtol=1e-4)
+    assert got["totalNeighbors"] == int(ref["nc"].astype(np.int64).sum())
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_step_vs_reference_golden(sx, fname):
+    ref = load_golden(fname)
+    got, _ = run_step_by_loops(sx, ref)
+    check_against_reference(got, ref)
+
+
+@pytest.mark.parametrize("fname", ["turb12_step0.npz", "noh14_step0.npz"])
+def test_fused_step_equals_loop_calls(sx, fname):
+    ref = load_golden(fname)
+    a, _ = run_step_by_loops(sx, ref)
+    hd = sx.sim.from_dump(ref)
+    calls = []
+    hd.hydro_step(halo=lambda arrs: calls.append(len(arrs)) or 0)
+    assert calls == [1, 6, 7, 1]  # the four halo exchanges of ve_hydro.hpp:154,165,174,185
+    for k in sx.sim.STEP_OUTPUTS:
+        np.testing.assert_array_equal(hd.get(k), a[k], err_msg=k)
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_step_vs_oracle_restatement(sx, oracle, fname):
+    """same inputs through the CPU restatement (bit-identical to the reference, tests/test_oracle.py)"""
+    d = load_golden(fname)
+    ref = oracle.hydro_step_f(d)
+    ngmax = int(d["ngmax"][0])
+    ref["nb_offsets"], ref["nb_sorted"] = csr_sorted_neighbors(ref["neighbors"], ref["nc"], ngmax)
+    ref["ngmax"] = d["ngmax"]
+    got, _ = run_step_by_loops(sx, d)
+    check_against_reference(got, ref)
+
+
+@pytest.mark.skipif(not have_ref_harness(), reason="oracle/_ref/ref_harness not present")
+@pytest.mark.parametrize("case,n,steps,hs", [("sedov", 50, 3, 1.0), ("noh", 40, 2, 1.0), ("turb", 32, 2, 1.4),
+                                             ("noh", 30, 1, 1.7)])
+def test_step_vs_compiled_reference(sx, tmp_path, case, n, steps, hs):
+    """the reference itself (BASELINE config 0 is `sedov -n 50`), every dumped step"""
+    dumps = run_ref_harness(case, n, steps, tmp_path / "o", hscale=hs)
+    for d in dumps:
+        ngmax = int(d["ngmax"][0])
+        d["nb_offsets"], d["nb_sorted"] = csr_sorted_neighbors(d["neighbors"], d["nc"], ngmax)
+        got, _ = run_step_by_loops(sx, d)
+        check_against_reference(got, d)
+
+
+def _random_points(n, box, seed, gaussian):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array(box[0::2]), np.array(box[1::2])
+    p = rng.normal(0.5, 0.15, size=(n, 3)).clip(0.0, 1.0 - 1e-12) if gaussian else rng.random((n, 3))
+    return (lo + p * (hi - lo)).T.copy()
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+@pytest.mark.parametrize("box", [[0., 1., 0., 1., 0., 1.], [-1.2, 0.23, -0.213, 3.213, -5.1, 1.23]])
+@pytest.mark.parametrize("radius,n,gaussian", [(0.124, 2500, False), (0.0624, 2500, True), (3.0, 500, False)])
+def test_find_neighbors_equals_all_to_all(sx, oracle, radius, n, gaussian, box, boundary):
+    """domain/test/unit/neighbors/findneighbors.cpp:43-133 with the GPU search (cstone::findNeighbors call shape)."""
+    import ctypes as C
+    x, y, z = _random_points(n, box, seed=n + boundary, gaussian=gaussian)
+    t = sx.host.build_tree(x, y, z, box, [boundary] * 3, bucket_size=64)
+    x, y, z = x[t.order], y[t.order], z[t.order]
+    h = np.full(n, radius / 2, np.float32)
+    ngmax = n
+    nb, cnt = sx.sim.find_neighbors(x, y, z, h, sx.sim.DeviceTree(t, "cuda:0"), box, [boundary] * 3, ngmax)
+    L, P = oracle.lib(), oracle.P
+    obox = oracle.make_box(box, [boundary] * 3)
+    nb_a = np.zeros(n * ngmax, np.uint32)
+    nc_a = np.zeros(n, np.uint32)
+    L.orc_all2all_neighbors_f(P(x), P(y), P(z), P(h), C.c_uint(n), P(nb_a), P(nc_a), C.c_uint(ngmax), C.byref(obox))
+    np.testing.assert_array_equal(cnt, nc_a)
+    _, ia = csr_sorted_neighbors(nb_a, nc_a + 1, ngmax)
+    _, ig = csr_sorted_neighbors(nb, cnt + 1, ngmax)
+    np.testing.assert_array_equal(ig, ia)
+
+
+def test_edge_cases(sx):
+    """empty range, ragged last group, ngmax truncation semantics, error codes"""
+    d = load_golden("turb12_step0.npz")
+    n = int(d["n"][0])
+    t = sx.sim.DeviceTree(d, "cuda:0")
+    # empty range
+    nb, cnt = sx.sim.find_neighbors(d["x"], d["y"], d["z"], d["h"], t, d["box"], d["boundary"], 150, first=5, last=5)
+    assert nb.size == 0 and cnt.size == 0
+    # ragged sub-range not aligned to 32: same counts as the full search
+    _, cnt_full = sx.sim.find_neighbors(d["x"], d["y"], d["z"], d["h"], t, d["box"], d["boundary"], 150)
+    _, cnt_sub = sx.sim.find_neighbors(d["x"], d["y"], d["z"], d["h"], t, d["box"], d["boundary"], 150, first=7,
+                                       last=n - 13)
+    np.testing.assert_array_equal(cnt_sub, cnt_full[7:n - 13])
+    np.testing.assert_array_equal(cnt_full + 1, d["nc"])
+    # ngmax smaller than the count: count keeps counting, list is truncated (findneighbors.hpp:119-121)
+    nb8, cnt8 = sx.sim.find_neighbors(d["x"], d["y"], d["z"], d["h"], t, d["box"], d["boundary"], 8)
+    np.testing.assert_array_equal(cnt8, cnt_full)
+    # ng0 > ngmax -> error as in sph/find_neighbors.hpp:52
+    hd = sx.sim.from_dump(d)
+    hd.p.ng0, hd.p.ngmax = 200, 150
+    with pytest.raises(sx.SphxError) as e:
+        hd.find_neighbors_xmass()
+    assert e.value.code == 3
+    # workspace too small
+    hd = sx.sim.from_dump(d)
+    hd.workspace = hd.workspace[:1024]
+    with pytest.raises(sx.SphxError) as e:
+        hd.find_neighbors_xmass()
+    assert e.value.code == 4
+
+
+def test_properties_at_scale(sx):
+    """Sedov 100^3 lattice (1M particles), no oracle needed: every particle of the periodic lattice has exactly 92
+    neighbours + self, neighbour relation is symmetric for equal h, the lattice at rest has zero
+    divv/curlv and uniform kx, and total energy rate sum(m du) vanishes."""
+    from sphexa_b200 import cases
+    n = 100
+    hd = cases.make_sedov(sx, n)
+    r = hd.hydro_step()
+    N = n ** 3
+    nc = hd.get("nc")
+    assert nc.min() == 93 and nc.max() == 93
+    assert r.totalNeighbors == 93 * N
+    kx = hd.get("kx")
+    assert np.abs(kx / kx.mean() - 1).max() < 1e-5
+    assert np.abs(hd.get("divv")).max() == 0.0 or np.abs(hd.get("divv")).max() < 1e-3
+    # symmetry of the neighbour relation on a sample of particles
+    nb = hd.export_neighbors().reshape(N, hd.p.ngmax)[:, :92]
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, N, 200):
+        for j in nb[i, :8]:
+            assert i in nb[j]
+    # momentum conservation: sum of m*a vanishes to rounding
+    ax = hd.get("ax").astype(np.float64)
+    assert abs(ax.sum()) < 1e-6 * np.abs(ax).sum() + 1e-30
