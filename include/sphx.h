@@ -252,6 +252,11 @@ extern "C"
     void sphx_hilbert_keys_host(const double* x, const double* y, const double* z, size_t n, const SphxBox* box,
                                 uint64_t* keys);
 
+    /* sph::updateH (sph/include/sph/kernels.hpp:26-32), T = float: host evaluation of exactly the arithmetic the
+     * device uses (bit-exact emulation of glibc powf, csrc/sphx_powf.h), exported for verification against libm. */
+    float sphx_update_h_host(unsigned ng0, unsigned nc, float h);
+    float sphx_powf_host(float x, float y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,8 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_ve_def_gradh", "sphx_eos",
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
-           "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host"]
+           "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
+           "sphx_powf_host"]
 
 
 class SphxError(RuntimeError):
@@ -87,6 +88,10 @@ def load():
     L.sphx_host_tree_sizes.argtypes = [C.c_void_p, C.c_void_p]
     L.sphx_host_tree_get.argtypes = [C.c_void_p] * 11
     L.sphx_hilbert_keys_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.sphx_update_h_host.restype = C.c_float
+    L.sphx_update_h_host.argtypes = [C.c_uint, C.c_uint, C.c_float]
+    L.sphx_powf_host.restype = C.c_float
+    L.sphx_powf_host.argtypes = [C.c_float, C.c_float]
     L.sphx_make_tables_host.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_find_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "sphx.h"
+#include "sphx_powf.h"
 
 namespace
 {
@@ -335,6 +336,9 @@ void sphx_host_tree_get(const SphxHostTree* t, unsigned* order, uint64_t* keys, 
     cp(internalToLeaf, t->internalToLeaf), cp(levelRange, t->levelRange), cp(leaves, t->leaves), cp(layout, t->layout);
     cp(centers, t->centers), cp(sizes, t->sizes);
 }
+
+float sphx_update_h_host(unsigned ng0, unsigned nc, float h) { return sphx::updateHExact(ng0, nc, h); }
+float sphx_powf_host(float x, float y) { return sphx::glibcPowf(x, y); }
 
 /* -------------------------------------------- kernel tables -------------------------------------------- */
 

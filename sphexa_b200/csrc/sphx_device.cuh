@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "sphx.h"
+#include "sphx_powf.h"
 
 namespace sphx
 {
@@ -70,17 +71,8 @@ __device__ __forceinline__ double minDistComp(double d, double s)
     return __dmul_rn(v, 0.5);
 }
 
-/*! @brief sph::updateH (sph/include/sph/kernels.hpp:26-32) for T = float
- *
- * glibc powf is correctly rounded in all but ~1e-9 of cases; CUDA powf is not (4-8 ulp), and a different last bit of
- * h changes the search radius. Evaluate pow in double (<= 2 ulp of double) and round once.
- */
-__device__ __forceinline__ float updateH(unsigned ng0, unsigned nc, float h)
-{
-    float base = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(1023.0f, float(ng0)), float(nc)));
-    float pw   = float(pow(double(base), double(0.1f)));
-    return __fmul_rn(__fmul_rn(h, 0.5f), pw);
-}
+//! sph::updateH (sph/include/sph/kernels.hpp:26-32) for T = float, bit-exact with the reference CPU (sphx_powf.h)
+__device__ __forceinline__ float updateH(unsigned ng0, unsigned nc, float h) { return updateHExact(ng0, nc, h); }
 
 //! lt::lookup (sph/include/sph/table_lookup.hpp:13-26), T = float
 __device__ __forceinline__ float tableLookup(const float* __restrict__ table, float v)

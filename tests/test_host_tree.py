@@ -108,3 +108,25 @@ def test_shuffled_input_is_sorted_back():
     np.testing.assert_array_equal(g["x"][perm][t.order], g["x"])
     np.testing.assert_array_equal(t.keys, g["keys"])
     np.testing.assert_array_equal(t.layout, g["tree_layout"])
+
+
+def test_powf_emulation_matches_libm():
+    """csrc/sphx_powf.h restates glibc's powf (FMA variant); the device uses the same code for sph::updateH.
+    Compare with the libm of this box on the argument range updateH produces and on a wide random range."""
+    L = sx.load()
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(0)
+    ng0 = np.float32(100)
+    bases = np.float32(1) + np.float32(1023.0) * ng0 / np.arange(1, 20000, dtype=np.float32)
+    xs = np.concatenate([bases, rng.uniform(1, 2e5, 20000).astype(np.float32),
+                         np.exp(rng.uniform(np.log(1e-30), np.log(1e30), 10000)).astype(np.float32)])
+    for x in xs:
+        assert L.sphx_powf_host(float(x), 0.1) == libm.powf(float(x), np.float32(0.1)), x
+    # sph::updateH itself against the oracle restatement (which calls libm)
+    import oracle_lib
+    O = oracle_lib.lib()
+    for nc in list(range(1, 400)) + [1000, 12345]:
+        for h in (0.0123456, 0.5, 3.3e-4):
+            assert L.sphx_update_h_host(100, nc, h) == O.orc_update_h_f(100, nc, h), (nc, h)
