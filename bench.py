@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — SPH-VE hydro-step throughput (particles/s) on B200, BASELINE.json metric.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libsphx.so, CUDA sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own OpenMP CPU build on the host cores
+
+A "step" is one pass of the hot path over all particles: neighbour search + h-iteration + XMass, VeDefGradh, EOS,
+IAD + divv/curlv, AV switches, momentum + energy (HydroVeProp::computeForces without Domain::sync,
+main/src/propagator/ve_hydro.hpp:147-190), on the synthetic Sedov lattice of SURVEY §8(d).
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "sph_hydro_step_particles_per_sec"
+UNIT = "particles/s"
+
+# algorithmic (compulsory) bytes per particle and loop: every field read once / written once, neighbour gathers and
+# the neighbour list NOT counted. Mixed precision, avClean = false, ideal gas via temp.
+ALGO_BYTES = {"find_neighbors_xmass": 44, "ve_def_gradh": 44, "eos": 32, "iad_divv_curlv": 80, "av_switches": 88,
+              "momentum_energy": 108}
+PHASES = list(ALGO_BYTES)
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref/sphexa_ref = unmodified sources, OpenMP)
+# ------------------------------------------------------------------------------------------------------------------
+REF_PHASE_LABELS = ["FindNeighbors", "XMass", "Normalization & Gradh", "EquationOfState", "IadVelocityDivCurl",
+                    "AVswitches", "MomentumAndEnergy"]
+
+
+def run_reference_cpu(side: int, steps: int, warmup: int) -> dict:
+    """Time `sphexa_ref --init sedov -n side -s (warmup+steps) --ascii` and parse its per-phase timer lines
+    (main/src/propagator/ve_hydro.hpp:135-191). Hydro-step time = FindNeighbors + the six loops (no domain::sync)."""
+    exe = REPO / "oracle" / "_ref" / "sphexa_ref"
+    cores = os.cpu_count() or 1
+    if not exe.exists():
+        raise FileNotFoundError(f"{exe} missing (built by __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run([str(exe), "--init", "sedov", "-n", str(side), "-s", str(warmup + steps), "--ascii"],
+                             cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             check=True).stdout
+    iters, cur = [], {}
+    for line in out.splitlines():
+        m = re.match(r"# (.+?): ([0-9.eE+-]+)s", line)
+        if m and m.group(1) in REF_PHASE_LABELS:
+            cur[m.group(1)] = cur.get(m.group(1), 0.0) + float(m.group(2))
+        if line.startswith("=== Total time for iteration"):
+            iters.append(cur)
+            cur = {}
+    timed = iters[warmup:warmup + steps]
+    if not timed:
+        raise RuntimeError("no timed iterations parsed from sphexa_ref output")
+    per_step = [sum(it.values()) for it in timed]
+    t = sum(per_step) / len(per_step)
+    n = side ** 3
+    phases = {k: sum(it.get(k, 0.0) for it in timed) / len(timed) * 1e3 for k in REF_PHASE_LABELS}
+    try:
+        cpu_model = next(l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except (OSError, StopIteration):
+        cpu_model = "unknown"
+    return {"value": n / t, "ms_per_step": t * 1e3, "cores": cores, "kind": "reference", "cpu_model": cpu_model,
+            "sample": f"sphexa_ref --init sedov -n {side} -s {warmup + steps} --ascii ({n} particles, OpenMP "
+                      f"{cores} threads, first {warmup} iterations dropped); step = FindNeighbors + 6 loops",
+            "phases_ms": phases, "n_particles": n}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    side = args.ref_side
+    r = run_reference_cpu(side, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64 (mixed, reference production types)",
+            "data": "synthetic",
+            "config": {"workload": f"Sedov blast wave {args.side}^3 (reference CPU arm runs the bounded sample "
+                                   f"Sedov {side}^3, same per-particle work)", "sample_side": side},
+            "cpu_baseline": {k: r[k] for k in ("value", "cores", "kind", "sample", "cpu_model")} | {"unit": UNIT},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "phases_ms": r["phases_ms"]}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def our_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsphx has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    import sphexa_b200 as sx
+    from sphexa_b200 import cases
+
+    sx.load()
+    side = args.side
+    # weak scaling: every rank holds its own Sedov side^3 box replica until the SFC domain decomposition lands
+    # (DESIGN.md §Multi-GPU); the data path has no collective yet.
+    t0 = time.time()
+    hd = cases.make_sedov(sx, side, device=dev)
+    setup_s = time.time() - t0
+    n = hd.n
+    stream = torch.cuda.current_stream()
+
+    calls = [("find_neighbors_xmass", lambda: hd.find_neighbors_xmass(sync=False)),
+             ("ve_def_gradh", hd.ve_def_gradh), ("eos", hd.eos),
+             ("iad_divv_curlv", lambda: hd.iad_divv_curlv(sync=False)), ("av_switches", hd.av_switches),
+             ("momentum_energy", lambda: hd.momentum_energy(sync=False))]
+    launches_per_step = 7  # reset-scalars + 6 loop kernels
+
+    h0 = hd.f["h"].clone()
+    alpha0 = hd.f["alpha"].clone()
+
+    def one_step(events=None):
+        # every step starts from the same state (h and alpha are in/out fields of the step)
+        hd.f["h"].copy_(h0)
+        hd.f["alpha"].copy_(alpha0)
+        for i, (_, fn) in enumerate(calls):
+            if events is not None:
+                events[i].record(stream)
+            fn()
+        if events is not None:
+            events[len(calls)].record(stream)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        one_step(ev[k])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    step_ms = [ev[k][0].elapsed_time(ev[k][-1]) for k in range(args.steps)]
+    total_ms = sum(step_ms)
+    phase_ms = {name: sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)) / args.steps
+                for i, (name, _) in enumerate(calls)}
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # step result (also proves the step ran): neighbour statistics + time steps
+    a = hd.args()
+    import ctypes as C
+    res = sx._cabi.SphxStepResult()
+    sx._cabi.check(hd.L.sphx_momentum_energy(C.byref(a), C.byref(res)))
+
+    # ---- end-to-end: host buffers in, host results out, through the same C-ABI calls -----------------------------
+    in_names = ["x", "y", "z", "h", "m", "vx", "vy", "vz", "temp", "alpha"]
+    out_names = ["ax", "ay", "az", "du", "h", "nc"]
+    host_in = {k: hd.f[k].cpu().pin_memory() for k in in_names}
+    host_in["h"] = h0.cpu().pin_memory()
+    host_in["alpha"] = alpha0.cpu().pin_memory()
+    host_out = {k: torch.empty_like(hd.f[k], device="cpu").pin_memory() for k in out_names}
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values()) + C.sizeof(sx._cabi.SphxStepResult)
+
+    def e2e_step():
+        for k in in_names:
+            hd.f[k].copy_(host_in[k], non_blocking=True)
+        for _, fn in calls[:-1]:
+            fn()
+        r = sx._cabi.SphxStepResult()
+        aa = hd.args()
+        sx._cabi.check(hd.L.sphx_momentum_energy(C.byref(aa), C.byref(r)))  # synchronises, returns dt scalars
+        for k in out_names:
+            host_out[k].copy_(hd.f[k], non_blocking=True)
+        torch.cuda.synchronize()
+        return r
+
+    e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / (float(e2e_ms.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    dom = max(phase_ms, key=phase_ms.get)
+    algo = ALGO_BYTES[dom] * n
+    achieved = algo / (phase_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tfile = REPO / "profiles" / "traffic.json"
+    if tfile.exists():
+        tj = json.loads(tfile.read_text())
+        traffic = tj.get(f"{dom}@sedov{side}")
+    mean_nc = res.totalNeighbors / n
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
+                "neighbor_list_bytes_per_particle": 4.0 * (mean_nc - 1),
+                "note": "algorithmic bytes = compulsory field traffic (SURVEY 8d), the stored neighbour list that "
+                        "this design reads in addition is reported separately",
+                "per_kernel": {k: {"ms": phase_ms[k], "GBps": ALGO_BYTES[k] * n / (phase_ms[k] * 1e-3) / 1e9,
+                                   "frac": ALGO_BYTES[k] * n / (phase_ms[k] * 1e-3) / 1e9 / peak} for k in PHASES}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference_cpu(args.ref_side, 2, 1)
+            cpu_baseline = {k: r[k] for k in ("value", "cores", "kind", "sample", "cpu_model")} | {"unit": UNIT}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                            "sample": f"unavailable: {e}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+f64 (mixed, reference production types)", "data": "synthetic",
+            "config": {"workload": f"Sedov blast wave {side}^3 ({n} particles per GPU), VE hydro step, ng0=100 "
+                                   f"ngmax=150, periodic box", "particles_per_gpu": n,
+                       "cache": "inputs (>3 GB of fields + neighbour list) exceed the 126 MB L2",
+                       "parallelism": f"{world} x independent box replica" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(e2e_ms.item())},
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "phases_ms": phase_ms,
+            "check": {"total_neighbors": int(res.totalNeighbors), "mean_nc": mean_nc, "max_nc": int(res.maxNc),
+                      "minDtCourant": res.minDtCourant, "minDtRho": res.minDtRho},
+            "setup_s": setup_s}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=200, help="Sedov lattice side (BASELINE config: 200)")
+    ap.add_argument("--ref-side", type=int, default=100, help="lattice side of the bounded CPU-reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()
