@@ -187,7 +187,7 @@ def our_arm(args):
              ("ve_def_gradh", hd.ve_def_gradh), ("eos", hd.eos),
              ("iad_divv_curlv", lambda: hd.iad_divv_curlv(sync=False)), ("av_switches", hd.av_switches),
              ("momentum_energy", lambda: hd.momentum_energy(sync=False))]
-    launches_per_step = 7  # reset-scalars + 6 loop kernels
+    launches_per_step = 13  # reset-scalars, block search, EOS, 5 x (work-counter reset + persistent loop kernel)
 
     h0 = hd.f["h"].clone()
     alpha0 = hd.f["alpha"].clone()
@@ -238,6 +238,8 @@ def our_arm(args):
     import ctypes as C
     res = sx._cabi.SphxStepResult()
     sx._cabi.check(hd.L.sphx_momentum_energy(C.byref(a), C.byref(res)))
+
+    bs = hd.block_stats()
 
     # ---- end-to-end: host buffers in, host results out, through the same C-ABI calls -----------------------------
     in_names = ["x", "y", "z", "h", "m", "vx", "vy", "vz", "temp", "alpha"]
@@ -324,7 +326,10 @@ def our_arm(args):
                     "ms_per_step": float(e2e_ms.item())},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "phases_ms": phase_ms,
             "check": {"total_neighbors": int(res.totalNeighbors), "mean_nc": mean_nc, "max_nc": int(res.maxNc),
-                      "minDtCourant": res.minDtCourant, "minDtRho": res.minDtRho},
+                      "minDtCourant": res.minDtCourant, "minDtRho": res.minDtRho,
+                      "candidates_per_block_mean": float(bs["numCand"].mean()),
+                      "candidates_per_block_max": int(bs["numCand"].max()),
+                      "candidates_per_particle": bs["candTop"] / n, "fold_blocks": int((bs["flags"] & 1).sum())},
             "setup_s": setup_s}
     print(json.dumps(line))
     if world > 1:

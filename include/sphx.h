@@ -186,6 +186,12 @@ extern "C"
      * Replaces cstone::allocateNcStacks (traversal/find_neighbors.cuh:492-505). */
     size_t sphx_workspace_bytes(size_t numAssigned, unsigned ngmax);
 
+    /* diagnostics: byte offsets of the workspace sections for (numAssigned, ngmax):
+     * out[0] step scalars, [1] block descriptors (40 B each: double origin[3], u32 candBegin, numCand, flags, pad),
+     * [2] neighbour list (uint4 vectors of eight 16-bit candidate indices), [3] candidate array (float4 records),
+     * [4] total bytes, [5] number of blocks, [6] list vectors per target (ceil(ngmax/8)), [7] candidate capacity */
+    void sphx_workspace_layout(size_t numAssigned, unsigned ngmax, size_t out[8]);
+
     /* host: kernel tables and normalisation constant, sinc^n kernel
      * (ParticlesData::createTables particles_data.hpp:380-387; sph_kernel_tables.hpp:77-101,144-172) */
     int sphx_make_tables_host(double sincIndex, float* wh_host, float* whd_host, double* K);

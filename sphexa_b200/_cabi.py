@@ -53,7 +53,7 @@ STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ER
           5: "SPHX_ERR_H_CONVERGENCE", 6: "SPHX_ERR_NGMAX_OVERFLOW", 7: "SPHX_ERR_TRAVERSAL", 8: "SPHX_ERR_NCCL"}
 
 # every symbol include/sphx.h declares
-EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_workspace_bytes",
+EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_workspace_bytes", "sphx_workspace_layout",
            "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_ve_def_gradh", "sphx_eos",
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
@@ -82,6 +82,8 @@ def load():
     L.sphx_last_error.restype = C.c_char_p
     L.sphx_workspace_bytes.restype = C.c_size_t
     L.sphx_workspace_bytes.argtypes = [C.c_size_t, C.c_uint]
+    L.sphx_workspace_layout.restype = None
+    L.sphx_workspace_layout.argtypes = [C.c_size_t, C.c_uint, C.c_void_p]
     L.sphx_host_tree_build.restype = C.c_void_p
     L.sphx_host_tree_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint]
     L.sphx_host_tree_free.argtypes = [C.c_void_p]

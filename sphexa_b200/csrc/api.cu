@@ -7,7 +7,7 @@
 #include <cstring>
 #include <string>
 
-#include "sphx_device.cuh"
+#include "sphx_block.cuh"
 #include "sphx_kernels.h"
 
 namespace
@@ -35,28 +35,32 @@ int cudaFail(cudaError_t e, const char* what)
 
 size_t numGroupsOf(size_t n) { return (n + sphx::kGroupSize - 1) / sphx::kGroupSize; }
 
-size_t listBytes(size_t numAssigned, unsigned ngmax)
+//! v1 list of the generic search: u32 particle indices, lane-interleaved ELL
+size_t genericListBytes(size_t numAssigned, unsigned ngmax)
 {
     return numGroupsOf(numAssigned) * size_t(ngmax) * sphx::kGroupSize * sizeof(unsigned);
 }
 
 struct Workspace
 {
-    sphx::StepScalars* scal;
-    unsigned*          list;
+    sphx::StepScalars*    scal;
+    sphx::WorkspaceLayout layout;
+    Workspace() : scal(nullptr), layout(0, 8) {}
 };
 
 int carve(const SphxStepArgs* a, Workspace& w)
 {
     if (!a) return fail(SPHX_ERR_INVALID, "null args");
     if (a->last < a->first || a->last > a->numLocal) return fail(SPHX_ERR_INVALID, "bad [first,last) range");
+    if (a->numLocal >= (size_t(1) << 32)) return fail(SPHX_ERR_INVALID, "more than 2^32 local particles");
     if (!a->workspace) return fail(SPHX_ERR_INVALID, "null workspace");
-    size_t need = sphx_workspace_bytes(a->last - a->first, a->p.ngmax);
-    if (a->workspaceBytes < need)
-        return fail(SPHX_ERR_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+    if (a->p.ngmax == 0 || a->p.ngmax > sphx::kMaxNgmaxStep)
+        return fail(SPHX_ERR_INVALID, "ngmax must be in [1, " + std::to_string(sphx::kMaxNgmaxStep) + "]");
+    w.layout = sphx::WorkspaceLayout(a->last - a->first, a->p.ngmax);
+    if (a->workspaceBytes < w.layout.total)
+        return fail(SPHX_ERR_WORKSPACE, "workspace too small: need " + std::to_string(w.layout.total) + " bytes");
     if (reinterpret_cast<uintptr_t>(a->workspace) % 16 != 0) return fail(SPHX_ERR_INVALID, "workspace not 16B aligned");
     w.scal = reinterpret_cast<sphx::StepScalars*>(a->workspace);
-    w.list = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + sphx::kScalarsBytes);
     return SPHX_OK;
 }
 
@@ -86,6 +90,8 @@ int errFlagsToStatus(unsigned flags)
         return fail(SPHX_ERR_TRAVERSAL, "GPU traversal stack exhausted in neighbor search");
     if (flags & sphx::kErrHConv) return fail(SPHX_ERR_H_CONVERGENCE, "coupled nc/h-updated failed to converge");
     if (flags & sphx::kErrNgmax) return fail(SPHX_ERR_NGMAX_OVERFLOW, "neighbour count exceeds ngmax after h-iteration");
+    if (flags & sphx::kErrCandSpace)
+        return fail(SPHX_ERR_WORKSPACE, "candidate array of the workspace exhausted (more than 16 candidates per particle)");
     return SPHX_OK;
 }
 
@@ -121,7 +127,14 @@ int sphx_device_check(void)
 
 size_t sphx_workspace_bytes(size_t numAssigned, unsigned ngmax)
 {
-    return sphx::kScalarsBytes + listBytes(numAssigned, ngmax);
+    return sphx::WorkspaceLayout(numAssigned, ngmax).total;
+}
+
+void sphx_workspace_layout(size_t numAssigned, unsigned ngmax, size_t out[8])
+{
+    sphx::WorkspaceLayout w(numAssigned, ngmax);
+    out[0] = w.scalOff, out[1] = w.blocksOff, out[2] = w.listOff, out[3] = w.candOff, out[4] = w.total;
+    out[5] = w.numBlocks, out[6] = w.nkbMax, out[7] = w.candCapacity;
 }
 
 int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r)
@@ -135,8 +148,8 @@ int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r)
     REQUIRE(a->f.xm); REQUIRE(a->wh);
     auto s = static_cast<cudaStream_t>(a->stream);
     sphx::launchResetScalars(w.scal, s);
-    sphx::launchFindNeighborsXmass(*a, w.list, w.scal, s);
-    SPHX_CUDA(cudaGetLastError());
+    SPHX_CUDA(sphx::launchBlockSearch(*a, w.layout, s));
+    SPHX_CUDA(sphx::launchXMass(*a, w.layout, s));
     if (r)
     {
         sphx::StepScalars h;
@@ -153,8 +166,7 @@ int sphx_ve_def_gradh(const SphxStepArgs* a)
     Workspace w;
     if (int rc = carve(a, w)) return rc;
     REQUIRE(a->f.xm); REQUIRE(a->f.kx); REQUIRE(a->f.gradh); REQUIRE(a->wh); REQUIRE(a->whd); REQUIRE(a->f.nc);
-    sphx::launchVeDefGradh(*a, w.list, static_cast<cudaStream_t>(a->stream));
-    SPHX_CUDA(cudaGetLastError());
+    SPHX_CUDA(sphx::launchVeDefGradh(*a, w.layout, static_cast<cudaStream_t>(a->stream)));
     return SPHX_OK;
 }
 
@@ -178,8 +190,7 @@ int sphx_iad_divv_curlv(const SphxStepArgs* a, SphxStepResult* r)
     REQUIRE(a->f.vx); REQUIRE(a->f.vy); REQUIRE(a->f.vz); REQUIRE(a->f.xm); REQUIRE(a->f.kx); REQUIRE(a->f.c11);
     REQUIRE(a->f.c12); REQUIRE(a->f.c13); REQUIRE(a->f.c22); REQUIRE(a->f.c23); REQUIRE(a->f.c33); REQUIRE(a->f.divv);
     auto s = static_cast<cudaStream_t>(a->stream);
-    sphx::launchIadDivvCurlv(*a, w.list, w.scal, s);
-    SPHX_CUDA(cudaGetLastError());
+    SPHX_CUDA(sphx::launchIadDivvCurlv(*a, w.layout, s));
     if (r)
     {
         sphx::StepScalars h;
@@ -195,8 +206,7 @@ int sphx_av_switches(const SphxStepArgs* a)
     Workspace w;
     if (int rc = carve(a, w)) return rc;
     REQUIRE(a->f.c); REQUIRE(a->f.divv); REQUIRE(a->f.alpha); REQUIRE(a->f.c11);
-    sphx::launchAvSwitches(*a, w.list, static_cast<cudaStream_t>(a->stream));
-    SPHX_CUDA(cudaGetLastError());
+    SPHX_CUDA(sphx::launchAvSwitches(*a, w.layout, static_cast<cudaStream_t>(a->stream)));
     return SPHX_OK;
 }
 
@@ -209,8 +219,7 @@ int sphx_momentum_energy(const SphxStepArgs* a, SphxStepResult* r)
     REQUIRE(a->f.du);
     if (a->p.avClean) { REQUIRE(a->f.dV11); }
     auto s = static_cast<cudaStream_t>(a->stream);
-    sphx::launchMomentumEnergy(*a, w.list, w.scal, s);
-    SPHX_CUDA(cudaGetLastError());
+    SPHX_CUDA(sphx::launchMomentumEnergy(*a, w.layout, s));
     if (r)
     {
         sphx::StepScalars h;
@@ -282,7 +291,7 @@ int sphx_find_neighbors(const double* x, const double* y, const double* z, const
     auto   s = static_cast<cudaStream_t>(stream);
     size_t n = last - first;
     void*  tmp = nullptr;
-    SPHX_CUDA(cudaMallocAsync(&tmp, sphx_workspace_bytes(n, ngmax), s));
+    SPHX_CUDA(cudaMallocAsync(&tmp, sphx::kScalarsBytes + genericListBytes(n, ngmax), s));
     auto* scal = reinterpret_cast<sphx::StepScalars*>(tmp);
     auto* list = reinterpret_cast<unsigned*>(static_cast<char*>(tmp) + sphx::kScalarsBytes);
     sphx::launchResetScalars(scal, s);
@@ -305,8 +314,7 @@ int sphx_export_neighbors(const SphxStepArgs* a, unsigned* neighbors_dev)
     Workspace w;
     if (int rc = carve(a, w)) return rc;
     REQUIRE(neighbors_dev); REQUIRE(a->f.nc);
-    sphx::launchExportNeighbors(unsigned(a->last - a->first), a->p.ngmax, w.list, a->f.nc + a->first, true,
-                                neighbors_dev, static_cast<cudaStream_t>(a->stream));
+    sphx::launchExportBlockNeighbors(*a, w.layout, neighbors_dev, static_cast<cudaStream_t>(a->stream));
     SPHX_CUDA(cudaGetLastError());
     return SPHX_OK;
 }

@@ -1,17 +1,16 @@
 /*! @file
- * Neighbour search over the cornerstone octree, fused with the coupled h-iteration and the XMass loop.
+ * Generic neighbour search with the cstone::findNeighbors call shape (any ngmax, particle-index lists, no h-iteration):
+ * the utility behind sphx_find_neighbors. The hydro step itself uses the block search in search.cu.
  *
  * Replaces (reference paths relative to /root/reference):
  *   cstone::findNeighbors            domain/include/cstone/findneighbors.hpp:77-170   (the predicate we must match)
- *   sph::findNeighborsSph            sph/include/sph/find_neighbors.hpp:11-44        (h-iteration)
- *   sph::cuda::computeXMass          sph/include/sph/hydro_ve/xmass_gpu.cu:57-129
  *   cstone::traverseNeighbors        domain/include/cstone/traversal/find_neighbors.cuh:182-489 (not followed)
  *
- * Design (B200-first, not a port): one warp owns 32 SFC-consecutive targets, one per lane. The octree is walked with
+ * Design: one warp owns 32 SFC-consecutive targets, one per lane. The octree is walked with
  * a per-warp stack in shared memory, 32 nodes per step, pruned with the bounding box of the warp's 2h-spheres. Every
  * leaf that survives is tested per lane with the reference CPU's own point<->cell criterion, its particles are staged
  * in shared memory and broadcast to all lanes, and hits are appended to the lane's column of a lane-interleaved ELL
- * list that stays in HBM for the other four loops of the step (the reference GPU path re-searches in every loop).
+ * list.
  * The pair predicate is evaluated in un-contracted fp64 exactly as the reference CPU does, so counts and sets are
  * bit-exact; the order inside a list is traversal order (compare after sorting).
  */
@@ -248,79 +247,6 @@ __device__ unsigned searchWithHIteration(Target& t, unsigned i, const DevBox& bo
     return ncSph;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    findNeighborsXmassKernel(unsigned first, unsigned last, DevBox box, SphxTreeView tree, const double* __restrict__ x,
-                             const double* __restrict__ y, const double* __restrict__ z, float* __restrict__ h,
-                             const float* __restrict__ m, const float* __restrict__ wh, unsigned* __restrict__ nc,
-                             float* __restrict__ xm, double K, unsigned ng0, unsigned ngmax,
-                             unsigned* __restrict__ list, StepScalars* scal)
-{
-    __shared__ WarpShared shared[kWarpsPerBlock];
-    const unsigned        warpInBlock = threadIdx.x >> 5;
-    const unsigned        lane        = laneId();
-    const size_t          group       = size_t(blockIdx.x) * kWarpsPerBlock + warpInBlock;
-    const size_t          numGroups   = (size_t(last - first) + kGroupSize - 1) / kGroupSize;
-    if (group >= numGroups) { return; }
-
-    WarpShared& sm = shared[warpInBlock];
-    unsigned    i  = first + unsigned(group) * kGroupSize + lane;
-
-    Target t;
-    t.valid = i < last;
-    unsigned il = t.valid ? i : last - 1;
-    t.x = x[il], t.y = y[il], t.z = z[il], t.h = h[il];
-
-    unsigned* listCol = list + nbListIndex(group, ngmax, 0, lane);
-    bool      hChanged;
-    unsigned  ncSph = searchWithHIteration(t, i, box, tree, x, y, z, ng0, ngmax, listCol, sm, scal, true, hChanged);
-
-    // statistics (conserved_quantities.hpp:146-157 sums nc)
-    unsigned ncv    = t.valid ? ncSph : 0;
-    unsigned ncSum  = ncv;
-    unsigned ncMax  = ncv;
-    unsigned nIter  = (t.valid && hChanged) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        ncSum += __shfl_xor_sync(kFullMask, ncSum, o);
-        ncMax = max(ncMax, __shfl_xor_sync(kFullMask, ncMax, o));
-        nIter += __shfl_xor_sync(kFullMask, nIter, o);
-    }
-    if (lane == 0)
-    {
-        atomicAdd(&scal->totalNeighbors, (unsigned long long)ncSum);
-        atomicMax(&scal->maxNc, ncMax);
-        if (nIter) { atomicAdd(&scal->numHIterated, nIter); }
-    }
-
-    if (!t.valid) { return; }
-    if (hChanged) { h[i] = t.h; }
-    nc[i] = ncSph;
-
-    // XMass (hydro_ve/xmass_kern.hpp:51-79) on the list just built
-    __syncwarp(__activemask());
-    unsigned ncCapped = min(ncSph - 1, ngmax);
-    float    hi       = t.h;
-    float    mi       = m[i];
-    float    hInv     = float(1.0 / double(hi));
-    float    h3Inv    = hInv * hInv * hInv;
-    float    twoH     = 2.0f * hi;
-    float    rho0i    = mi;
-    for (unsigned k = 0; k < ncCapped; ++k)
-    {
-        unsigned j  = listCol[size_t(k) * kGroupSize];
-        float    xx = float(t.x - x[j]);
-        float    yy = float(t.y - y[j]);
-        float    zz = float(t.z - z[j]);
-        applyPBC(box, twoH, xx, yy, zz);
-        float dist = sqrtf(xx * xx + yy * yy + zz * zz);
-        float vloc = dist * hInv;
-        float w    = tableLookup(wh, vloc);
-        rho0i += w * m[j];
-    }
-    xm[i] = float(double(mi) / (double(rho0i) * K * double(h3Inv)));
-}
-
 /*! @brief cstone::findNeighbors batch shape: ngmax-strided lists and counts, no h-iteration */
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     findNeighborsKernel(unsigned first, unsigned last, DevBox box, SphxTreeView tree, const double* __restrict__ x,
@@ -369,22 +295,14 @@ __global__ void resetScalarsKernel(StepScalars* s)
     s->maxNc          = 0;
     s->numHIterated   = 0;
     s->errFlags       = 0;
+    s->candTop        = 0;
+    for (int q = 0; q < 8; ++q)
+        s->work[q] = 0;
 }
 
 /* ---------------------------------------------- launchers ---------------------------------------------- */
 
 void launchResetScalars(StepScalars* s, cudaStream_t stream) { resetScalarsKernel<<<1, 1, 0, stream>>>(s); }
-
-void launchFindNeighborsXmass(const SphxStepArgs& a, unsigned* list, StepScalars* scal, cudaStream_t stream)
-{
-    unsigned n = unsigned(a.last - a.first);
-    if (n == 0) return;
-    unsigned numGroups = (n + kGroupSize - 1) / kGroupSize;
-    unsigned blocks    = (numGroups + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    findNeighborsXmassKernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-        unsigned(a.first), unsigned(a.last), makeDevBox(a.box), a.tree, a.f.x, a.f.y, a.f.z, a.f.h, a.f.m, a.wh, a.f.nc,
-        a.f.xm, a.p.K, a.p.ng0, a.p.ngmax, list, scal);
-}
 
 void launchFindNeighbors(const double* x, const double* y, const double* z, const float* h, unsigned first,
                          unsigned last, const SphxBox& box, const SphxTreeView& tree, unsigned ngmax, unsigned* list,

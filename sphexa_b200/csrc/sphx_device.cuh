@@ -163,13 +163,15 @@ struct StepScalars
     unsigned long long totalNeighbors;
     unsigned           maxNc;
     unsigned           numHIterated;
-    unsigned           errFlags; // bit0: h non-convergence, bit1: ngmax overflow, bit2: traversal stack overflow
-    unsigned           pad;
+    unsigned           errFlags; // bit0: h non-convergence, bit1: ngmax overflow, bit2: traversal overflow, bit3: cand
+    unsigned           candTop;  // bump allocator of the candidate array (block search)
+    unsigned           work[8];  // dynamic work counters of the persistent loop kernels
 };
 
 constexpr unsigned kErrHConv     = 1u;
 constexpr unsigned kErrNgmax     = 2u;
 constexpr unsigned kErrTraversal = 4u;
+constexpr unsigned kErrCandSpace = 8u;
 
 constexpr size_t kScalarsBytes = 256; // StepScalars + padding, keeps the list 256-byte aligned
 

@@ -10,18 +10,28 @@ namespace sphx
 
 struct StepScalars;
 
+struct WorkspaceLayout;
+
 void launchResetScalars(StepScalars* s, cudaStream_t stream);
-void launchFindNeighborsXmass(const SphxStepArgs& a, unsigned* list, StepScalars* scal, cudaStream_t stream);
+
+// generic search (neighbors.cu), v1 list format: u32 particle indices, lane-interleaved ELL
 void launchFindNeighbors(const double* x, const double* y, const double* z, const float* h, unsigned first,
                          unsigned last, const SphxBox& box, const SphxTreeView& tree, unsigned ngmax, unsigned* list,
                          unsigned* counts, StepScalars* scal, cudaStream_t stream);
 void launchExportNeighbors(unsigned numAssigned, unsigned ngmax, const unsigned* list, const unsigned* counts,
                            bool countsIncludeSelf, unsigned* out, cudaStream_t stream);
 
-void launchVeDefGradh(const SphxStepArgs& a, const unsigned* list, cudaStream_t s);
-void launchEos(const SphxStepArgs& a, cudaStream_t s);
-void launchIadDivvCurlv(const SphxStepArgs& a, const unsigned* list, StepScalars* scal, cudaStream_t s);
-void launchAvSwitches(const SphxStepArgs& a, const unsigned* list, cudaStream_t s);
-void launchMomentumEnergy(const SphxStepArgs& a, const unsigned* list, StepScalars* scal, cudaStream_t s);
+// block search of the hydro step (search.cu)
+size_t      searchSharedBytes(unsigned ngmax);
+cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t stream);
+void launchExportBlockNeighbors(const SphxStepArgs& a, const WorkspaceLayout& w, unsigned* out, cudaStream_t stream);
+
+// particle loops (loops.cu)
+cudaError_t launchXMass(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+cudaError_t launchVeDefGradh(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+void        launchEos(const SphxStepArgs& a, cudaStream_t s);
+cudaError_t launchIadDivvCurlv(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+cudaError_t launchAvSwitches(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+cudaError_t launchMomentumEnergy(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 
 } // namespace sphx

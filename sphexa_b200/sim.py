@@ -181,6 +181,19 @@ class HydroData:
         _cabi.check(self.L.sphx_hydro_step(C.byref(a), cb, None, C.byref(self.result) if sync else None))
         return self.result
 
+    def block_stats(self) -> dict:
+        """diagnostics: per-block candidate counts and flags read back from the workspace"""
+        lay = np.zeros(8, np.uint64)
+        self.L.sphx_workspace_layout(self.last - self.first, self.p.ngmax, lay.ctypes.data)
+        nb = int(lay[5])
+        raw = self.workspace[int(lay[1]): int(lay[1]) + nb * 40].cpu().numpy()
+        desc = raw.view(np.dtype([("o", np.float64, 3), ("candBegin", np.uint32), ("numCand", np.uint32),
+                                  ("flags", np.uint32), ("pad", np.uint32)]))
+        scal = self.workspace[:64].cpu().numpy()
+        return dict(numCand=desc["numCand"].copy(), flags=desc["flags"].copy(), origin=desc["o"].copy(),
+                    candBegin=desc["candBegin"].copy(), candTop=int(scal[28:32].view(np.uint32)[0]),
+                    errFlags=int(scal[24:28].view(np.uint32)[0]), candCapacity=int(lay[7]))
+
     def export_neighbors(self) -> np.ndarray:
         out = torch.zeros((self.last - self.first) * self.p.ngmax, dtype=torch.int32, device=self.device)
         a = self.args()

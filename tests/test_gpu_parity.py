@@ -35,9 +35,12 @@ def sx():
 FAMILIES = [("c11", "c12", "c13", "c22", "c23", "c33"), ("divv", "curlv"), ("ax", "ay", "az")]
 
 
-# du = K prho_i sum_j m_j a_mom (v_ij . A_ij): in near-uniform subsonic flow the pair terms cancel to < 1 % of their
-# magnitude, so du gets a floor of 1e-1 x max|du| (absolute error allowed 1e-5 of the field scale; measured 4e-6).
-FLOOR_FRACTION = {"du": 1e-1}
+# du = K prho_i sum_j m_j a_mom (v_ij . A_ij) and a = -K sum_j (pressure-gradient pair terms): in near-uniform subsonic
+# flow (turbulence box: u = 1000, Mach 0.3) the ~100 pair terms cancel to < 1 % of their magnitude, and two fp32
+# evaluations that add them in a different order (the reference CPU's list order vs. our four interleaved partial sums)
+# differ by that summation noise. These fields get a floor of 1e-1 x the family max-norm, i.e. the absolute error allowed
+# for a nearly cancelled value is 1e-5 of the field scale (measured: 4e-6 du, 1.4e-6 ax).
+FLOOR_FRACTION = {"du": 1e-1, "ax": 1e-1, "ay": 1e-1, "az": 1e-1}
 
 
 def field_floor(ref: dict, k: str) -> float:
