@@ -144,7 +144,8 @@ def reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64 (mixed, reference production types)",
             "data": "synthetic",
-            "config": {"workload": f"Sedov blast wave {args.side}^3 (reference CPU arm runs the bounded sample "
+            "config": {"workload": f"Sedov blast wave {args.side or int(round(200 * args.gpus ** (1.0 / 3.0)))}^3 "
+                                   f"(reference CPU arm runs the bounded sample "
                                    f"Sedov {side}^3, same per-particle work)", "sample_side": side},
             "cpu_baseline": {k: r[k] for k in ("value", "cores", "kind", "sample", "cpu_model")} | {"unit": UNIT},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -168,26 +169,50 @@ def our_arm(args):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL for the device-side plumbing of the bench (barriers, max-over-ranks), gloo for the host-side object
+        # gathers of the domain decomposition; the halo exchange itself is libsphx's own NCCL communicator
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device(dev))
 
     import sphexa_b200 as sx
     from sphexa_b200 import cases
+    from sphexa_b200 import dist as sdist
 
     sx.load()
-    side = args.side
-    # weak scaling: every rank holds its own Sedov side^3 box replica until the SFC domain decomposition lands
-    # (DESIGN.md §Multi-GPU); the data path has no collective yet.
+    # weak scaling: 8 M particles per GPU. N = 1 is BASELINE config 1 (Sedov 200^3), N = 8 is config 4 (Sedov 400^3);
+    # the global lattice is cut into N contiguous Hilbert-key ranges, each rank holds its range plus halos.
+    side = args.side if args.side else int(round(200 * world ** (1.0 / 3.0)))
     t0 = time.time()
-    hd = cases.make_sedov(sx, side, device=dev)
+    dh = None
+    if world == 1:
+        hd = cases.make_sedov(sx, side, device=dev)
+        n_assigned = hd.n
+    else:
+        dh = sdist.DistributedHydro(sx.sim, cases.sedov_global(side), rank, world, dev)
+        hd = dh.hd
+        n_assigned = dh.n_assigned
     setup_s = time.time() - t0
-    n = hd.n
+    n_global = side ** 3
+    n = hd.n  # local particles including halos
     stream = torch.cuda.current_stream()
 
-    calls = [("find_neighbors_xmass", lambda: hd.find_neighbors_xmass(sync=False)),
-             ("ve_def_gradh", hd.ve_def_gradh), ("eos", hd.eos),
-             ("iad_divv_curlv", lambda: hd.iad_divv_curlv(sync=False)), ("av_switches", hd.av_switches),
-             ("momentum_energy", lambda: hd.momentum_energy(sync=False))]
-    launches_per_step = 13  # reset-scalars, block search, EOS, 5 x (work-counter reset + persistent loop kernel)
+    # HydroVeProp::computeForces (ve_hydro.hpp:147-190): one C-ABI call per loop, halo exchanges in between
+    def X(*names):
+        return (lambda: dh.exchange(list(names))) if dh is not None else None
+
+    seq = [("find_neighbors_xmass", lambda: hd.find_neighbors_xmass(sync=False), X("xm")),
+           ("ve_def_gradh", hd.ve_def_gradh, None),
+           ("eos", hd.eos, X("vx", "vy", "vz", "prho", "c", "kx")),
+           ("iad_divv_curlv", lambda: hd.iad_divv_curlv(sync=False), X("c11", "c12", "c13", "c22", "c23", "c33", "divv")),
+           ("av_switches", hd.av_switches, X("alpha")),
+           ("momentum_energy", lambda: hd.momentum_energy(sync=False), None)]
+    calls = []
+    for name, fn, ex in seq:
+        calls.append((name, fn))
+        if ex is not None:
+            calls.append(("halo_exchange", ex))
+    num_exchanges = sum(1 for c in calls if c[0] == "halo_exchange")
+    # reset-scalars, block search, EOS, 5 x (work-counter reset + persistent loop kernel), pack kernel per exchange
+    launches_per_step = 13 + num_exchanges
 
     h0 = hd.f["h"].clone()
     alpha0 = hd.f["alpha"].clone()
@@ -224,14 +249,16 @@ def our_arm(args):
 
     step_ms = [ev[k][0].elapsed_time(ev[k][-1]) for k in range(args.steps)]
     total_ms = sum(step_ms)
-    phase_ms = {name: sum(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)) / args.steps
-                for i, (name, _) in enumerate(calls)}
+    phase_ms = {}
+    for i, (name, _) in enumerate(calls):
+        phase_ms[name] = phase_ms.get(name, 0.0) + sum(ev[k][i].elapsed_time(ev[k][i + 1])
+                                                       for k in range(args.steps)) / args.steps
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms = float(tmax.item())
     ms_per_step = total_ms / args.steps
-    value = n * world / (ms_per_step * 1e-3)
+    value = n_global / (ms_per_step * 1e-3)
 
     # step result (also proves the step ran): neighbour statistics + time steps
     a = hd.args()
@@ -255,7 +282,7 @@ def our_arm(args):
         for k in in_names:
             hd.f[k].copy_(host_in[k], non_blocking=True)
         for _, fn in calls[:-1]:
-            fn()
+            fn()  # the loops and, on N > 1, the NCCL halo exchanges between them
         r = sx._cabi.SphxStepResult()
         aa = hd.args()
         sx._cabi.check(hd.L.sphx_momentum_energy(C.byref(aa), C.byref(r)))  # synchronises, returns dt scalars
@@ -279,7 +306,7 @@ def our_arm(args):
     e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = n * world / (float(e2e_ms.item()) * 1e-3)
+    e2e_value = n_global / (float(e2e_ms.item()) * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -287,7 +314,8 @@ def our_arm(args):
         return
 
     peak, peak_src = measured_peaks()
-    dom = max(phase_ms, key=phase_ms.get)
+    dom = max(PHASES, key=lambda k: phase_ms[k])
+    n = n_assigned  # algorithmic bytes count the particles a rank computes
     algo = ALGO_BYTES[dom] * n
     achieved = algo / (phase_ms[dom] * 1e-3) / 1e9
     traffic = None
@@ -295,7 +323,7 @@ def our_arm(args):
     if tfile.exists():
         tj = json.loads(tfile.read_text())
         traffic = tj.get(f"{dom}@sedov{side}")
-    mean_nc = res.totalNeighbors / n
+    mean_nc = res.totalNeighbors / n_assigned
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
@@ -317,10 +345,12 @@ def our_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64 (mixed, reference production types)", "data": "synthetic",
-            "config": {"workload": f"Sedov blast wave {side}^3 ({n} particles per GPU), VE hydro step, ng0=100 "
-                                   f"ngmax=150, periodic box", "particles_per_gpu": n,
-                       "cache": "inputs (>3 GB of fields + neighbour list) exceed the 126 MB L2",
-                       "parallelism": f"{world} x independent box replica" if world > 1 else "single GPU"},
+            "config": {"workload": f"Sedov blast wave {side}^3 ({n_global} particles), VE hydro step, ng0=100 ngmax=150, "
+                                   f"periodic box", "particles_per_gpu": n_global // world,
+                       "local_particles_rank0_incl_halos": hd.n,
+                       "cache": "inputs (>3 GB of fields + neighbour list per GPU) exceed the 126 MB L2",
+                       "parallelism": (f"SFC (Hilbert) domain decomposition over {world} GPUs, 4 NCCL halo exchanges "
+                                       f"per step (send/recv), one process per GPU") if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(e2e_ms.item())},
@@ -342,7 +372,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--side", type=int, default=200, help="Sedov lattice side (BASELINE config: 200)")
+    ap.add_argument("--side", type=int, default=0,
+                    help="global Sedov lattice side; default 200 * gpus^(1/3): 200 on 1 GPU, 400 on 8 (BASELINE configs)")
     ap.add_argument("--ref-side", type=int, default=100, help="lattice side of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

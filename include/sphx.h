@@ -258,6 +258,65 @@ extern "C"
     void sphx_hilbert_keys_host(const double* x, const double* y, const double* z, size_t n, const SphxBox* box,
                                 uint64_t* keys);
 
+    /* --- SFC domain decomposition over the GPUs of one node (host side) --------------------------------- */
+
+    /* cstone::makeSfcAssignment / uniformBins (domain/include/cstone/domain/domaindecomp.hpp:33-110): contiguous
+     * Hilbert-key ranges balanced by particle count, rank boundaries on leaf boundaries of the global octree of
+     * bucketSize. sortedKeys: SFC-sorted keys of all n particles; splits[nranks + 1]: first particle of each rank. */
+    int sphx_sfc_assignment_host(const uint64_t* sortedKeys, size_t n, int nranks, unsigned bucketSize,
+                                 size_t* splits);
+
+    /* Halo discovery for the rank owning the SFC-sorted particles [ownedBegin, ownedEnd)
+     * (cstone Halos::discover, domain/include/cstone/halos/halos.hpp:131-192): whole-cell halos, i.e. every particle of
+     * a leaf (octree of bucketSize over all particles) that overlaps the box of an owned leaf inflated by
+     * 2 max(h in that leaf), PBC-aware. flags[n] must be zero-initialised; halo particles are set to 1. */
+    int sphx_find_halos_host(const double* x_host, const double* y_host, const double* z_host, const float* h_host,
+                             size_t n, const SphxBox* box, unsigned bucketSize, size_t ownedBegin, size_t ownedEnd,
+                             unsigned char* flags);
+
+    /* --- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ------------------------------------------------- */
+
+#define SPHX_UNIQUE_ID_BYTES 128
+    typedef struct SphxComm SphxComm;
+
+    /* NCCL bootstrap. Rank 0 calls sphx_comm_unique_id and distributes the 128 bytes through any host channel (the
+     * reference would use MPI_Bcast; bench.py and the tests use the torch.distributed store); then every rank calls
+     * sphx_comm_init with the CUDA device it will run on already current. NCCL is dlopen()ed at this point. */
+    int sphx_comm_unique_id(char id[SPHX_UNIQUE_ID_BYTES]);
+    int sphx_comm_init(SphxComm** comm, int rank, int nranks, const char id[SPHX_UNIQUE_ID_BYTES]);
+    int sphx_comm_free(SphxComm* comm);
+
+    /* Halo exchange plan of one rank = cstone's SendList + recv layout (domain/include/cstone/domain/layout.hpp,
+     * halos/halos.hpp:234-254) flattened: what this rank sends to each peer is a list of local particle indices
+     * (device array); what it receives from a peer is ONE contiguous range of its local arrays, because local arrays
+     * are SFC-sorted and the peer owns a contiguous key range. */
+    typedef struct SphxHaloPlan
+    {
+        int             numPeers;
+        const int*      peers;       /* host, numPeers: peer ranks */
+        const unsigned* sendOffsets; /* host, numPeers + 1: slice of sendIdx that goes to each peer */
+        const unsigned* sendIdx;     /* DEVICE, sendOffsets[numPeers] local particle indices */
+        const unsigned* recvBegin;   /* host, numPeers: first local index of the halo range filled by each peer */
+        const unsigned* recvCount;   /* host, numPeers */
+        void*           sendBuffer;  /* DEVICE scratch for the packed sends */
+        size_t          sendBufferBytes; /* >= sum over the arrays of one exchange of 16-aligned(numSend * elemBytes) */
+    } SphxHaloPlan;
+
+    /* Domain::exchangeHalos (domain/include/cstone/domain/domain.hpp:372-377; GPU path halos/exchange_halos_gpu.cuh:
+     * 34-119): pack the listed arrays' send lists with one gather kernel, then grouped ncclSend / ncclRecv; receives
+     * land directly in the halo ranges. Everything is enqueued on `stream`; no host synchronisation. count <= 8,
+     * elemBytes 4 or 8. */
+    int sphx_halo_exchange(SphxComm* comm, const SphxHaloPlan* plan, int count, void* const* arrays,
+                           const int* elemBytes, void* stream);
+
+    /* all-reduce of n <= 16 host doubles (op: 0 min, 1 max, 2 sum); replaces the MPI_Allreduce of the time step
+     * (sph/include/sph/ts_global.hpp:97-113) and of the neighbour statistics. Synchronises the stream. */
+    int sphx_allreduce_f64(SphxComm* comm, double* values_host, int n, int op, void* stream);
+
+    /* sphx_hydro_step with the four halo exchanges of HydroVeProp::computeForces (ve_hydro.hpp:154,165,174,185) done
+     * by sphx_halo_exchange and the result scalars reduced over all ranks (min dt, sum of neighbours, max nc). */
+    int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* comm, const SphxHaloPlan* plan, SphxStepResult* r);
+
     /* sph::updateH (sph/include/sph/kernels.hpp:26-32), T = float: host evaluation of exactly the arithmetic the
      * device uses (bit-exact emulation of glibc powf, csrc/sphx_powf.h), exported for verification against libm. */
     float sphx_update_h_host(unsigned ng0, unsigned nc, float h);

@@ -3,7 +3,7 @@
 The product is libsphx.so (CUDA sm_100a kernels + C ABI, include/sphx.h). This package is the thin Python plumbing
 used by tests and bench.py: ctypes bindings, torch tensors as device memory, torch.distributed for multi-GPU launch.
 """
-from . import _cabi, host  # noqa: F401
+from . import _cabi, dist, host  # noqa: F401
 
 try:  # torch is plumbing only; the host helpers work without it
     from . import sim  # noqa: F401

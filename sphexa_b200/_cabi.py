@@ -47,6 +47,14 @@ class SphxStepResult(C.Structure):
                 ("maxNc", C.c_uint), ("numHIterated", C.c_uint)]
 
 
+class SphxHaloPlan(C.Structure):
+    _fields_ = [("numPeers", C.c_int), ("peers", C.c_void_p), ("sendOffsets", C.c_void_p), ("sendIdx", C.c_void_p),
+                ("recvBegin", C.c_void_p), ("recvCount", C.c_void_p), ("sendBuffer", C.c_void_p),
+                ("sendBufferBytes", C.c_size_t)]
+
+
+UNIQUE_ID_BYTES = 128
+
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
 
 STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ERR_INVALID", 4: "SPHX_ERR_WORKSPACE",
@@ -58,7 +66,8 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
-           "sphx_powf_host"]
+           "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
+           "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist"]
 
 
 class SphxError(RuntimeError):
@@ -103,6 +112,15 @@ def load():
         getattr(L, name).argtypes = [C.c_void_p]
     L.sphx_export_neighbors.argtypes = [C.c_void_p, C.c_void_p]
     L.sphx_hydro_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_sfc_assignment_host.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_void_p]
+    L.sphx_find_halos_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint,
+                                       C.c_size_t, C.c_size_t, C.c_void_p]
+    L.sphx_comm_unique_id.argtypes = [C.c_void_p]
+    L.sphx_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.sphx_comm_free.argtypes = [C.c_void_p]
+    L.sphx_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.sphx_hydro_step_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

@@ -59,6 +59,30 @@ def sedov_fields(x, y, z, p: Params, r1=0.5, mTotal=1.0, width=0.1, u0=1e-8, ene
                 temp=ui / np.float64(cv), alpha=np.float32(p.alphamin))
 
 
+def sedov_global(side: int) -> dict:
+    """host-side description of the Sedov case (positions in generation order, per-particle fields, box, params):
+    input of dist.DistributedHydro"""
+    p = Params(minDt=1e-6, minDt_m1=1e-6, gamma=5.0 / 3.0, muiConst=10.0)
+    x, y, z = regular_grid(0.5, side)
+    return dict(x=x, y=y, z=z, fields=sedov_fields(x, y, z, p), params=p, box=[-0.5, 0.5] * 3, boundary=[1, 1, 1])
+
+
+def noh_global(side: int) -> dict:
+    """Noh implosion (see make_noh) as a host-side description"""
+    p = Params(minDt=1e-4, minDt_m1=1e-4, gamma=5.0 / 3.0, muiConst=10.0)
+    x, y, z = jittered_lattice(0.5, side)
+    keep = np.sqrt(x * x + y * y + z * z) <= 0.5
+    x, y, z = x[keep], y[keep], z[keep]
+    n = x.size
+    hInit = np.cbrt(3.0 / (4 * np.pi) * p.ng0 * (4.0 * np.pi / 3.0 * 0.5 ** 3) / n) * 0.5
+    cv = ideal_gas_cv(p.muiConst, p.gamma)
+    radius = np.maximum(np.sqrt(x * x + y * y + z * z), 1e-10)
+    f = dict(h=np.float32(hInit), m=np.float32(1.0 / n), temp=np.float64(1e-20) / np.float64(cv),
+             alpha=np.float32(p.alphamin), vx=(-1.0 * (x / radius)).astype(np.float32),
+             vy=(-1.0 * (y / radius)).astype(np.float32), vz=(-1.0 * (z / radius)).astype(np.float32))
+    return dict(x=x, y=y, z=z, fields=f, params=p, box=[-0.5, 0.5] * 3, boundary=[0, 0, 0])
+
+
 def make_sedov(sx, side: int, device="cuda:0") -> HydroData:
     """Sedov blast wave on a side^3 lattice, periodic box (-0.5, 0.5)^3 (sedov_init.hpp:98-131)."""
     p = Params(minDt=1e-6, minDt_m1=1e-6, gamma=5.0 / 3.0, muiConst=10.0)

@@ -107,6 +107,11 @@ void fillResult(const sphx::StepScalars& h, const SphxParams& p, SphxStepResult*
 
 } // namespace
 
+namespace sphx
+{
+void setLastError(const std::string& msg) { g_lastError = msg; }
+} // namespace sphx
+
 extern "C"
 {
 

@@ -337,6 +337,131 @@ void sphx_host_tree_get(const SphxHostTree* t, unsigned* order, uint64_t* keys, 
     cp(centers, t->centers), cp(sizes, t->sizes);
 }
 
+/* ------------------------------------ SFC domain decomposition (one node, N ranks) ------------------------------------ */
+
+/*! cstone::makeSfcAssignment / uniformBins (domain/include/cstone/domain/domaindecomp.hpp:33-110): contiguous Hilbert-key
+ *  ranges balanced by particle count; rank boundaries are boundaries of the leaves of the global octree of `bucketSize`.
+ *  Input: the SFC-sorted keys of ALL particles. Output: splits[r] = index of the first particle of rank r. */
+int sphx_sfc_assignment_host(const uint64_t* sortedKeys, size_t n, int nranks, unsigned bucketSize, size_t* splits)
+{
+    if (!sortedKeys || !splits || nranks < 1) return SPHX_ERR_INVALID;
+    // leaf boundaries of the converged bucketSize tree, as particle offsets: split key ranges top-down
+    std::vector<size_t> bounds; // particle offset of every leaf start, ascending
+    struct Range
+    {
+        uint64_t start;
+        int      level;
+        size_t   pBegin, pEnd;
+    };
+    std::vector<Range> stack{Range{0, 0, 0, n}};
+    while (!stack.empty())
+    {
+        Range r = stack.back();
+        stack.pop_back();
+        if (r.pEnd - r.pBegin <= bucketSize || r.level == kMaxLevel)
+        {
+            bounds.push_back(r.pBegin);
+            continue;
+        }
+        uint64_t childRange = uint64_t(1) << (3 * (kMaxLevel - r.level - 1));
+        size_t   cuts[9];
+        cuts[0] = r.pBegin, cuts[8] = r.pEnd;
+        for (int c = 1; c < 8; ++c)
+            cuts[c] = size_t(std::lower_bound(sortedKeys + cuts[c - 1], sortedKeys + r.pEnd,
+                                              r.start + uint64_t(c) * childRange) - sortedKeys);
+        for (int c = 7; c >= 0; --c) // push in reverse: leaves pop in SFC order
+            stack.push_back(Range{r.start + uint64_t(c) * childRange, r.level + 1, cuts[c], cuts[c + 1]});
+    }
+    bounds.push_back(n);
+    // uniformBins: cut at the leaf boundary closest to r * n / nranks
+    splits[0] = 0;
+    for (int r = 1; r < nranks; ++r)
+    {
+        size_t target = size_t((double(n) * r) / nranks);
+        auto   it     = std::lower_bound(bounds.begin(), bounds.end(), target);
+        size_t hiB = *it, loB = (it == bounds.begin()) ? 0 : *(it - 1);
+        size_t cut = (hiB - target < target - loB) ? hiB : loB;
+        splits[r]  = std::max(cut, splits[r - 1]);
+    }
+    splits[nranks] = n;
+    return SPHX_OK;
+}
+
+/*! Halo discovery for the rank that owns the SFC-sorted particles [ownedBegin, ownedEnd)
+ *  (cstone Halos::discover, domain/include/cstone/halos/halos.hpp:131-192 + traversal/collisions.hpp): every particle of a
+ *  leaf (octree of bucketSize over all particles) that overlaps the box of an owned leaf inflated by 2 max(h in that
+ *  leaf) is a halo: whole-cell halos, PBC-aware. flags[n]: set to 1 for halo particles (must be zero-initialised). */
+int sphx_find_halos_host(const double* x, const double* y, const double* z, const float* h, size_t n,
+                         const SphxBox* sbox, unsigned bucketSize, size_t ownedBegin, size_t ownedEnd,
+                         unsigned char* flags)
+{
+    if (!x || !y || !z || !h || !sbox || !flags || ownedEnd < ownedBegin || ownedEnd > n) return SPHX_ERR_INVALID;
+    SphxHostTree* t = sphx_host_tree_build(x, y, z, n, sbox, bucketSize);
+    for (size_t i = 0; i < n; ++i)
+        if (t->order[i] != i)
+        {
+            sphx_host_tree_free(t);
+            return SPHX_ERR_INVALID; // particles must be SFC-sorted
+        }
+    HBox       box(*sbox);
+    const bool pbc[3] = {sbox->boundary[0] == 1, sbox->boundary[1] == 1, sbox->boundary[2] == 1};
+    const double L[3] = {box.lx, box.ly, box.lz};
+
+    // owned leaves: [firstLeaf, lastLeaf)
+    int firstLeaf = int(std::upper_bound(t->layout.begin(), t->layout.end(), unsigned(ownedBegin)) - t->layout.begin()) - 1;
+    int lastLeaf  = int(std::lower_bound(t->layout.begin(), t->layout.end(), unsigned(ownedEnd)) - t->layout.begin());
+    std::vector<int> leafToNode(t->numLeaves);
+    for (int i = 0; i < t->numNodes; ++i)
+        if (t->childOffsets[i] == 0) leafToNode[t->internalToLeaf[i]] = i;
+
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int lf = firstLeaf; lf < lastLeaf; ++lf)
+    {
+        size_t pb = std::max<size_t>(t->layout[lf], ownedBegin), pe = std::min<size_t>(t->layout[lf + 1], ownedEnd);
+        if (pb >= pe) continue;
+        float hmax = 0;
+        for (size_t p = pb; p < pe; ++p)
+            hmax = std::max(hmax, h[p]);
+        int    nd = leafToNode[lf];
+        double c[3], sz[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            c[d]  = t->centers[3 * nd + d];
+            sz[d] = t->sizes[3 * nd + d] + 2.0 * double(hmax) * (1.0 + 1e-6);
+        }
+        int stack[512];
+        int sp      = 0;
+        stack[sp++] = 0;
+        while (sp > 0)
+        {
+            int  node    = stack[--sp];
+            bool overlap = true;
+            for (int d = 0; d < 3 && overlap; ++d)
+            {
+                double dd = t->centers[3 * node + d] - c[d];
+                if (pbc[d]) dd -= L[d] * std::rint(dd / L[d]);
+                overlap = std::fabs(dd) <= (t->sizes[3 * node + d] + sz[d]) * (1.0 + 1e-9);
+            }
+            if (!overlap) continue;
+            int child = t->childOffsets[node];
+            if (child == 0)
+            {
+                int    k  = t->internalToLeaf[node];
+                size_t qb = t->layout[k], qe = t->layout[k + 1];
+                for (size_t q = qb; q < qe; ++q)
+                    if (q < ownedBegin || q >= ownedEnd) flags[q] = 1;
+            }
+            else if (sp + 8 <= 512)
+            {
+                for (int cc = 0; cc < 8; ++cc)
+                    stack[sp++] = child + cc;
+            }
+        }
+    }
+    sphx_host_tree_free(t);
+    return SPHX_OK;
+}
+
 float sphx_update_h_host(unsigned ng0, unsigned nc, float h) { return sphx::updateHExact(ng0, nc, h); }
 float sphx_powf_host(float x, float y) { return sphx::glibcPowf(x, y); }
 

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <string>
+
 #include "sphx.h"
 
 namespace sphx
@@ -11,6 +13,9 @@ namespace sphx
 struct StepScalars;
 
 struct WorkspaceLayout;
+
+//! set the text returned by sphx_last_error() (api.cu)
+void setLastError(const std::string& msg);
 
 void launchResetScalars(StepScalars* s, cudaStream_t stream);
 
