@@ -61,7 +61,7 @@ extern "C"
     typedef struct SphxTreeView
     {
         int             numLeafNodes;
-        int             numNodes;
+        int             numNodes;       /* informational, may be 0 (OctreeNsView does not carry it) */
         const uint64_t* prefixes;       /* numNodes, Warren-Salmon placeholder-bit keys (may be NULL: unused here) */
         const int*      childOffsets;   /* numNodes */
         const int*      internalToLeaf; /* numNodes */

@@ -66,7 +66,7 @@ int carve(const SphxStepArgs* a, Workspace& w)
 
 int checkTree(const SphxTreeView& t)
 {
-    if (t.numNodes <= 0 || !t.childOffsets || !t.internalToLeaf || !t.layout || !t.centers || !t.sizes)
+    if (t.numLeafNodes <= 0 || !t.childOffsets || !t.internalToLeaf || !t.layout || !t.centers || !t.sizes)
         return fail(SPHX_ERR_INVALID, "incomplete tree view");
     return SPHX_OK;
 }
