@@ -28,7 +28,7 @@ namespace sphx
 {
 
 constexpr int kSearchThreads  = kBlockTargets;
-constexpr int kTileCap        = 768;   // staged particles per tile
+constexpr int kTileCap        = 768;   // staged particles per tile (incl. padding), multiple of 4
 constexpr int kMaxLeaves      = 512;   // leaves overlapping one block's bounding box
 constexpr int kMaxProvisional = 16384; // particles in those leaves (15-bit provisional index)
 constexpr int kMaxTiles       = 48;
@@ -36,7 +36,10 @@ constexpr int kFrontierCap    = 1024; // nodes per tree level that overlap the b
 
 struct SearchShared
 {
-    float4         tile[kTileCap + 4]; // +4: the test loop reads up to three entries past a leaf's end
+    // staged particles, SoA so that four consecutive x (y, z) are one 16-byte load and pair up for the packed
+    // f32x2 arithmetic; every leaf is padded to a multiple of four entries with far-away dummies
+    float          tileX[kTileCap], tileY[kTileCap], tileZ[kTileCap];
+    unsigned       tileJ[kTileCap]; // particle index, ~0u for padding
     unsigned       usedBits[kMaxProvisional / 32];
     unsigned short wordPrefix[kMaxProvisional / 32];
     int            leafKey[kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
@@ -72,7 +75,7 @@ struct SearchArgs
 
 size_t searchSharedBytes(unsigned ngmax)
 {
-    size_t hits = size_t(ngmax) * kBlockTargets * sizeof(unsigned short);
+    size_t hits = size_t(ngmax + 1) * kBlockTargets * sizeof(unsigned short); // + 1: the target's own particle
     size_t fr   = 2 * size_t(kFrontierCap) * sizeof(int);
     return sizeof(SearchShared) + (hits > fr ? hits : fr);
 }
@@ -116,9 +119,9 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
     unsigned short* hits     = reinterpret_cast<unsigned short*>(smemRaw + sizeof(SearchShared));
     int*            frontier = reinterpret_cast<int*>(hits); // [2][kFrontierCap], live only during the tree walk
     // node indices of the leaves, unsorted (traversal output) and sorted: live until the first tile is staged
-    int* leafNode = reinterpret_cast<int*>(s.tile);
-    int* leafTmp  = leafNode + kMaxLeaves;
-    static_assert(2 * kMaxLeaves * sizeof(int) <= sizeof(s.tile), "leaf scratch must fit into the tile");
+    int* leafNode = reinterpret_cast<int*>(s.tileX);
+    int* leafTmp  = reinterpret_cast<int*>(s.tileY);
+    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.tileX), "leaf scratch must fit into the tile");
 
     constexpr int T    = kBlockTargets;
     const int     t    = threadIdx.x;
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
 #pragma unroll 4
             for (int q = 0; q < L; ++q)
             {
-                const int c = s.leafKey[q];
+                const int c = (s.leafKey[q] + 3) & ~3; // padded to a multiple of four
                 if (c > kTileCap) err = 1;
                 if (tileCount + c > kTileCap)
                 {
@@ -349,8 +352,9 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
         // ---------------------------------------------------------------------------------------------------------
         // fp32 filter thresholds. |d2_fp32 - d2_exact| <= 2^-24 (7 r E + 6.5 r^2) near the decision boundary
         // (E bounds every relative coordinate); pairs inside the margin are decided by the exact predicate.
-        const float tx = float(xi - ox), ty = float(yi - oy), tz = float(zi - oz);
-        float       r2lo, r2hi;
+        const float  tx = float(xi - ox), ty = float(yi - oy), tz = float(zi - oz);
+        const float2 ntx = make_float2(-tx, -tx), nty = make_float2(-ty, -ty), ntz = make_float2(-tz, -tz);
+        float        r2lo, r2hi;
         {
             const float rr     = 2.0f * hi * 1.000001f;
             const float margin = 5.9604645e-8f * 16.0f * (rr * E + rr * rr);
@@ -360,14 +364,14 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
         }
 
         unsigned       slot    = t; // next free slot of this thread's hit column (index into hits)
-        const unsigned slotEnd = ngmax * T;
+        const unsigned slotEnd = (ngmax + 1) * T; // the hit column also receives the target's own particle
         const unsigned iBlock0 = a.first + blockIdx.x * T;
         for (int tIdx = 0; tIdx < nTiles; ++tIdx)
         {
             const int lb = s.tileFirstLeaf[tIdx], le = s.tileFirstLeaf[tIdx + 1];
             if (lb == le) continue;
             const int tileBase = s.leafP0[lb];
-            const int tileN    = s.leafP0[le - 1] + s.leafKey[le - 1] - tileBase;
+            const int tileN    = s.leafP0[le - 1] + ((s.leafKey[le - 1] + 3) & ~3) - tileBase;
 
             // stage
             {
@@ -375,18 +379,24 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
                 for (int p = t; p < tileN; p += T)
                 {
                     const int P = tileBase + p;
-                    while (P >= s.leafP0[l] + s.leafKey[l])
+                    while (P >= s.leafP0[l] + ((s.leafKey[l] + 3) & ~3))
                         ++l;
-                    const unsigned j = unsigned(s.leafFirst[l] + (P - s.leafP0[l]));
-                    s.tile[p]        = relativePosition(a, j, ox, oy, oz, foldMode);
-                    s.used8[p]       = 0;
-                    if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = P;
+                    const int off = P - s.leafP0[l];
+                    float4    rp  = make_float4(1e18f, 1e18f, 1e18f, __uint_as_float(~0u)); // padding: never a hit
+                    if (off < s.leafKey[l])
+                    {
+                        const unsigned j = unsigned(s.leafFirst[l] + off);
+                        rp               = relativePosition(a, j, ox, oy, oz, foldMode);
+                        if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = P;
+                    }
+                    s.tileX[p] = rp.x, s.tileY[p] = rp.y, s.tileZ[p] = rp.z;
+                    s.tileJ[p] = __float_as_uint(rp.w);
+                    s.used8[p] = 0;
                 }
             }
             __syncthreads();
 
-            const unsigned slotTile  = slot;
-            const int      selfLocal = s.selfP[t] - tileBase; // this target's own entry, if it is in this tile
+            const unsigned slotTile = slot;
             for (int l = lb; l < le; ++l)
             {
                 // does any sphere of this warp touch the leaf?
@@ -399,37 +409,48 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
 
                 const int pb = s.leafP0[l] - tileBase;
                 const int pe = pb + s.leafKey[l];
-                // four staged particles per step, straight-line: the four distance chains overlap
+                // four staged particles per step in straight-line code; distances in packed f32x2 arithmetic
                 for (int p = pb; p < pe; p += 4)
                 {
-                    float4 q[4];
-                    float  d2[4];
-                    bool   h[4];
-                    bool   anyAmb = false;
+                    const float4 X = *reinterpret_cast<const float4*>(&s.tileX[p]);
+                    const float4 Y = *reinterpret_cast<const float4*>(&s.tileY[p]);
+                    const float4 Z = *reinterpret_cast<const float4*>(&s.tileZ[p]);
+                    const float2 dx0 = __fadd2_rn(make_float2(X.x, X.y), ntx), dx1 = __fadd2_rn(make_float2(X.z, X.w), ntx);
+                    const float2 dy0 = __fadd2_rn(make_float2(Y.x, Y.y), nty), dy1 = __fadd2_rn(make_float2(Y.z, Y.w), nty);
+                    const float2 dz0 = __fadd2_rn(make_float2(Z.x, Z.y), ntz), dz1 = __fadd2_rn(make_float2(Z.z, Z.w), ntz);
+                    const float2 s0 = __ffma2_rn(dz0, dz0, __ffma2_rn(dy0, dy0, __fmul2_rn(dx0, dx0)));
+                    const float2 s1 = __ffma2_rn(dz1, dz1, __ffma2_rn(dy1, dy1, __fmul2_rn(dx1, dx1)));
+                    const float  d2[4] = {s0.x, s0.y, s1.x, s1.y};
+                    // a pair is a sure hit below r2lo and a sure miss from r2hi on; in between (or in fold mode) the
+                    // reference's exact fp64 predicate decides. The target's own particle (d2 = 0) is recorded like
+                    // any other hit and dropped when the list is written.
+                    bool amb = false;
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        q[u] = s.tile[p + u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                        amb = amb | (!(d2[u] < r2lo) & (d2[u] < r2hi));
+                    if (__any_sync(kFullMask, amb))
                     {
-                        const float dx = q[u].x - tx, dy = q[u].y - ty, dz = q[u].z - tz;
-                        d2[u]  = dx * dx + dy * dy + dz * dz;
-                        h[u]   = d2[u] < r2hi && p + u < pe;
-                        anyAmb = anyAmb || (h[u] && !(d2[u] < r2lo));
-                    }
-                    if (__any_sync(kFullMask, anyAmb))
-                    {
-                        // inside the fp32 error margin (or fold mode): the reference's exact fp64 predicate decides
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            if (h[u] && !(d2[u] < r2lo))
-                                h[u] = exactPair(a.x, a.y, a.z, __float_as_uint(q[u].w), xi, yi, zi, usePbc, box,
-                                                 radiusSq);
+                        {
+                            bool h = d2[u] < r2hi;
+                            if (h && !(d2[u] < r2lo))
+                            {
+                                const unsigned j = s.tileJ[p + u];
+                                h = j != ~0u && exactPair(a.x, a.y, a.z, j, xi, yi, zi, usePbc, box, radiusSq);
+                            }
+                            if (h)
+                            {
+                                if (slot < slotEnd) hits[slot] = (unsigned short)(tileBase + p + u);
+                                slot += T;
+                            }
+                        }
+                        continue;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                     {
-                        const bool hit = h[u] && (p + u != selfLocal);
+                        const bool hit = d2[u] < r2lo;
                         if (hit && slot < slotEnd) hits[slot] = (unsigned short)(tileBase + p + u);
                         slot += hit ? unsigned(T) : 0u;
                     }
@@ -452,7 +473,9 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
             __syncthreads();
         }
 
-        count = (slot - t) / T; // keeps counting beyond ngmax, as the reference does
+        // number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
+        count = (slot - t) / T;
+        if (valid && s.selfP[t] >= 0 && count > 0) --count;
 
         // ---------------------------------------------------------------------------------------------------------
         // sph/find_neighbors.hpp:17-36: while ((ngmin > nc || nc - 1 > ngmax) && iteration++ < 10)
@@ -544,7 +567,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
         int l = 0;
         for (int P = t; P < pEnd; P += T)
         {
-            while (l < L && P >= s.leafP0[l] + s.leafKey[l])
+            while (l < L && P >= s.leafP0[l] + ((s.leafKey[l] + 3) & ~3))
                 ++l;
             if (l >= L) break;
             if (P < s.leafP0[l]) continue; // alignment gap between tiles
@@ -558,8 +581,10 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
 
     // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets
     {
-        const unsigned kc  = haveSpace ? min(count, ngmax) : 0u;
-        const unsigned nkb = (kc + 7) / 8;
+        const unsigned kc     = haveSpace ? min(count, ngmax) : 0u;
+        const unsigned nkb    = (kc + 7) / 8;
+        const unsigned selfPu = unsigned(s.selfP[t]); // provisional index of the target itself (never < 0 if valid)
+        unsigned       rk     = 0;                    // read cursor in the hit column
         uint4* lp = a.list + (size_t(blockIdx.x) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
         for (unsigned kb = 0; kb < nkb; ++kb)
         {
@@ -571,7 +596,9 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
                 unsigned       e = 0;
                 if (k < kc)
                 {
-                    const unsigned P = hits[k * T + t];
+                    unsigned P = hits[rk * T + t];
+                    if (P == selfPu) P = hits[++rk * T + t];
+                    ++rk;
                     const unsigned w = s.usedBits[P >> 5];
                     e                = s.wordPrefix[P >> 5] + __popc(w & ((1u << (P & 31)) - 1u));
                 }
