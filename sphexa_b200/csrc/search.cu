@@ -73,12 +73,7 @@ struct SearchArgs
     StepScalars*  scal;
 };
 
-size_t searchSharedBytes(unsigned ngmax)
-{
-    size_t hits = size_t(ngmax + 1) * kBlockTargets * sizeof(unsigned short); // + 1: the target's own particle
-    size_t fr   = 2 * size_t(kFrontierCap) * sizeof(int);
-    return sizeof(SearchShared) + (hits > fr ? hits : fr);
-}
+size_t searchSharedBytes(unsigned) { return sizeof(SearchShared); }
 
 //! the reference's pair predicate (findneighbors.hpp:33-60,117,134), every fp64 operation rounded separately
 __device__ __forceinline__ bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
@@ -112,20 +107,34 @@ __device__ __forceinline__ float4 relativePosition(const SearchArgs& a, unsigned
 }
 
 template<bool IterateH>
-__global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __grid_constant__ SearchArgs a)
+__global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __grid_constant__ SearchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    SearchShared&   s        = *reinterpret_cast<SearchShared*>(smemRaw);
-    unsigned short* hits     = reinterpret_cast<unsigned short*>(smemRaw + sizeof(SearchShared));
-    int*            frontier = reinterpret_cast<int*>(hits); // [2][kFrontierCap], live only during the tree walk
-    // node indices of the leaves, unsorted (traversal output) and sorted: live until the first tile is staged
-    int* leafNode = reinterpret_cast<int*>(s.tileX);
-    int* leafTmp  = reinterpret_cast<int*>(s.tileY);
-    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.tileX), "leaf scratch must fit into the tile");
+    SearchShared& s = *reinterpret_cast<SearchShared*>(smemRaw);
+    // scratch of the tree walk, aliased onto arrays that are written only later:
+    int* frontier = reinterpret_cast<int*>(s.tileX);    // [2][kFrontierCap]: until the first tile is staged
+    int* leafNode = reinterpret_cast<int*>(s.leafBox);  // leaves in traversal order: until they are ranked
+    int* leafTmp  = reinterpret_cast<int*>(s.usedBits); // node index of the ranked leaves: until the leaf boxes exist
+    static_assert(2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX) + sizeof(s.tileJ), "frontier scratch");
+    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.leafBox), "leaf scratch");
+    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.usedBits) + sizeof(s.wordPrefix), "ranked-leaf scratch");
+    static_assert(offsetof(SearchShared, tileY) == offsetof(SearchShared, tileX) + sizeof(s.tileX) &&
+                      offsetof(SearchShared, wordPrefix) == offsetof(SearchShared, usedBits) + sizeof(s.usedBits),
+                  "aliased arrays must be contiguous");
+
+
 
     constexpr int T    = kBlockTargets;
     const int     t    = threadIdx.x;
     const int     lane = t & 31, warp = t >> 5;
+
+    /* Hit columns. Provisional hits of thread t = (warp g, lane) go to row k of the group's slice of the final list
+     * storage, hitCol[k * 32] (u16, 64 bytes per row and group): L2-resident scratch instead of 38 KB of shared memory
+     * per CTA, which more than doubles the number of resident CTAs. The list writer converts the slice in place, warp
+     * synchronously: the final vector (kb, lane) covers exactly provisional rows 8 kb .. 8 kb + 7 (see there). */
+    unsigned short* const hitCol =
+        reinterpret_cast<unsigned short*>(a.list + (size_t(blockIdx.x) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize) +
+        lane;
     const unsigned i     = a.first + blockIdx.x * T + t;
     const bool     valid = i < a.last;
     const unsigned il    = valid ? i : a.last - 1;
@@ -363,8 +372,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
             if (!valid) r2lo = r2hi = -1.0f;
         }
 
-        unsigned       slot    = t; // next free slot of this thread's hit column (index into hits)
-        const unsigned slotEnd = (ngmax + 1) * T; // the hit column also receives the target's own particle
+        unsigned       slot    = 0;                     // next free element of this thread's hit column (row * 32)
+        const unsigned slotEnd = (ngmax + 1) * kGroupSize; // the column also receives the target's own particle
         const unsigned iBlock0 = a.first + blockIdx.x * T;
         for (int tIdx = 0; tIdx < nTiles; ++tIdx)
         {
@@ -441,8 +450,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
                             }
                             if (h)
                             {
-                                if (slot < slotEnd) hits[slot] = (unsigned short)(tileBase + p + u);
-                                slot += T;
+                                if (slot < slotEnd) hitCol[slot] = (unsigned short)(tileBase + p + u);
+                                slot += kGroupSize;
                             }
                         }
                         continue;
@@ -451,8 +460,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
                     for (int u = 0; u < 4; ++u)
                     {
                         const bool hit = d2[u] < r2lo;
-                        if (hit && slot < slotEnd) hits[slot] = (unsigned short)(tileBase + p + u);
-                        slot += hit ? unsigned(T) : 0u;
+                        if (hit && slot < slotEnd) hitCol[slot] = (unsigned short)(tileBase + p + u);
+                        slot += hit ? kGroupSize : 0u;
                     }
                 }
             }
@@ -460,8 +469,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
             // mark the staged particles this thread kept
             {
                 const unsigned kEnd = min(slot, slotEnd);
-                for (unsigned k = slotTile; k < kEnd; k += T)
-                    s.used8[hits[k] - tileBase] = 1;
+                for (unsigned k = slotTile; k < kEnd; k += kGroupSize)
+                    s.used8[hitCol[k] - tileBase] = 1;
             }
             __syncthreads();
             for (int base = warp * 32; base < tileN; base += kSearchThreads)
@@ -474,7 +483,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
         }
 
         // number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
-        count = (slot - t) / T;
+        count = slot / kGroupSize;
         if (valid && s.selfP[t] >= 0 && count > 0) --count;
 
         // ---------------------------------------------------------------------------------------------------------
@@ -581,12 +590,17 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
 
     // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets
     {
+        /* In-place, warp-synchronous: provisional row k of the group occupies bytes [64 k, 64 k + 64) of its slice,
+         * the final vector (kb, lane) bytes [512 kb + 16 lane, + 16), i.e. a piece of provisional row 8 kb + lane / 4.
+         * All lanes first read their rows 8 kb .. 8 kb + 8 (one extra when the own particle has been skipped), then
+         * all lanes write their vector kb, which only destroys rows 8 kb .. 8 kb + 7 that every lane has consumed. */
         const unsigned kc     = haveSpace ? min(count, ngmax) : 0u;
         const unsigned nkb    = (kc + 7) / 8;
-        const unsigned selfPu = unsigned(s.selfP[t]); // provisional index of the target itself (never < 0 if valid)
-        unsigned       rk     = 0;                    // read cursor in the hit column
+        const unsigned nkbW   = warpMaxU(nkb);
+        const unsigned selfPu = unsigned(s.selfP[t]); // provisional index of the target itself
+        unsigned       rk     = 0;                    // read cursor (row) in the hit column
         uint4* lp = a.list + (size_t(blockIdx.x) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
-        for (unsigned kb = 0; kb < nkb; ++kb)
+        for (unsigned kb = 0; kb < nkbW; ++kb)
         {
             unsigned wds[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -596,15 +610,17 @@ __global__ void __launch_bounds__(kSearchThreads, 3) blockSearchKernel(const __g
                 unsigned       e = 0;
                 if (k < kc)
                 {
-                    unsigned P = hits[rk * T + t];
-                    if (P == selfPu) P = hits[++rk * T + t];
+                    unsigned P = hitCol[rk * kGroupSize];
+                    if (P == selfPu) P = hitCol[++rk * kGroupSize];
                     ++rk;
                     const unsigned w = s.usedBits[P >> 5];
                     e                = s.wordPrefix[P >> 5] + __popc(w & ((1u << (P & 31)) - 1u));
                 }
                 wds[q >> 1] |= e << (16 * (q & 1));
             }
-            lp[size_t(kb) * kGroupSize] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            __syncwarp();
+            if (kb < nkb) lp[size_t(kb) * kGroupSize] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            __syncwarp();
         }
     }
 
@@ -665,6 +681,7 @@ static cudaError_t configureSearch(unsigned ngmax)
 {
     static size_t configured = 0;
     size_t        bytes      = searchSharedBytes(ngmax);
+    if (bytes <= 48 * 1024) return cudaSuccess;
     if (bytes > configured)
     {
         cudaError_t e = cudaFuncSetAttribute(blockSearchKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

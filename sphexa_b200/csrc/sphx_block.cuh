@@ -47,7 +47,8 @@ __host__ __device__ inline unsigned numBlocksOf(size_t numAssigned)
 {
     return unsigned((numAssigned + kBlockTargets - 1) / kBlockTargets);
 }
-__host__ __device__ inline unsigned nkbMaxOf(unsigned ngmax) { return (ngmax + 7u) / 8u; }
+//! 8-entry list vectors per target; one spare entry: the search also records the target's own particle provisionally
+__host__ __device__ inline unsigned nkbMaxOf(unsigned ngmax) { return (ngmax + 8u) / 8u; }
 __host__ __device__ inline size_t   alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 //! workspace carving, shared by api.cu and the kernels' launchers

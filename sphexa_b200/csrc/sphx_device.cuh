@@ -129,6 +129,14 @@ __device__ __forceinline__ double warpMax(double v)
     return v;
 }
 
+__device__ __forceinline__ unsigned warpMaxU(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = max(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+
 __device__ __forceinline__ float warpMinF(float v)
 {
 #pragma unroll
