@@ -202,6 +202,11 @@ extern "C"
      * Replaces sph::findNeighborsSfc (sph/find_neighbors.hpp:46-56, a no-op on the reference GPU path) +
      * sph::cuda::computeXMass (hydro_ve/xmass_gpu.cu:104-129). */
     int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r);
+    /* the two halves of the above, for callers that keep the reference's split: sph::findNeighborsSfc
+     * (sph/find_neighbors.hpp:46-56: search + h-iteration, writes h, nc and the list) and sph::computeXMass proper
+     * (hydro_ve/xmass.hpp:39-74: xm from the stored list) */
+    int sphx_find_neighbors_sph(const SphxStepArgs* a, SphxStepResult* r);
+    int sphx_xmass(const SphxStepArgs* a);
 
     /* sph::cuda::computeVeDefGradh (hydro_ve/ve_def_gradh_gpu.cu:50-97): kx, gradh */
     int sphx_ve_def_gradh(const SphxStepArgs* a);

@@ -62,7 +62,7 @@ STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ER
 
 # every symbol include/sphx.h declares
 EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_workspace_bytes", "sphx_workspace_layout",
-           "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_ve_def_gradh", "sphx_eos",
+           "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_find_neighbors_sph", "sphx_xmass", "sphx_ve_def_gradh", "sphx_eos",
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
@@ -106,9 +106,9 @@ def load():
     L.sphx_make_tables_host.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_find_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
-    for name in ("sphx_find_neighbors_xmass", "sphx_iad_divv_curlv", "sphx_momentum_energy"):
+    for name in ("sphx_find_neighbors_xmass", "sphx_find_neighbors_sph", "sphx_iad_divv_curlv", "sphx_momentum_energy"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
-    for name in ("sphx_ve_def_gradh", "sphx_eos", "sphx_av_switches"):
+    for name in ("sphx_ve_def_gradh", "sphx_eos", "sphx_av_switches", "sphx_xmass"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.sphx_export_neighbors.argtypes = [C.c_void_p, C.c_void_p]
     L.sphx_hydro_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -142,23 +142,50 @@ void sphx_workspace_layout(size_t numAssigned, unsigned ngmax, size_t out[8])
     out[5] = w.numBlocks, out[6] = w.nkbMax, out[7] = w.candCapacity;
 }
 
-int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r)
+int sphx_find_neighbors_sph(const SphxStepArgs* a, SphxStepResult* r)
 {
     if (int rc = sphx_device_check()) return rc;
     Workspace w;
     if (int rc = carve(a, w)) return rc;
     if (int rc = checkTree(a->tree)) return rc;
     if (a->p.ng0 > a->p.ngmax) return fail(SPHX_ERR_INVALID, "ng0 should be smaller than ngmax");
-    REQUIRE(a->f.x); REQUIRE(a->f.y); REQUIRE(a->f.z); REQUIRE(a->f.h); REQUIRE(a->f.m); REQUIRE(a->f.nc);
-    REQUIRE(a->f.xm); REQUIRE(a->wh);
+    REQUIRE(a->f.x); REQUIRE(a->f.y); REQUIRE(a->f.z); REQUIRE(a->f.h); REQUIRE(a->f.nc);
     auto s = static_cast<cudaStream_t>(a->stream);
     sphx::launchResetScalars(w.scal, s);
     SPHX_CUDA(sphx::launchBlockSearch(*a, w.layout, s));
-    SPHX_CUDA(sphx::launchXMass(*a, w.layout, s));
     if (r)
     {
         sphx::StepScalars h;
         if (int rc = readScalars(w, s, h)) return rc;
+        fillResult(h, a->p, r);
+        return errFlagsToStatus(h.errFlags);
+    }
+    return SPHX_OK;
+}
+
+int sphx_xmass(const SphxStepArgs* a)
+{
+    if (int rc = sphx_device_check()) return rc;
+    Workspace w;
+    if (int rc = carve(a, w)) return rc;
+    REQUIRE(a->f.m); REQUIRE(a->f.xm); REQUIRE(a->f.nc); REQUIRE(a->wh);
+    SPHX_CUDA(sphx::launchXMass(*a, w.layout, static_cast<cudaStream_t>(a->stream)));
+    return SPHX_OK;
+}
+
+int sphx_find_neighbors_xmass(const SphxStepArgs* a, SphxStepResult* r)
+{
+    if (int rc = sphx_device_check()) return rc;
+    if (!a) return fail(SPHX_ERR_INVALID, "null args");
+    REQUIRE(a->f.m); REQUIRE(a->f.xm); REQUIRE(a->wh);
+    if (int rc = sphx_find_neighbors_sph(a, nullptr)) return rc;
+    if (int rc = sphx_xmass(a)) return rc;
+    if (r)
+    {
+        Workspace w;
+        if (int rc = carve(a, w)) return rc;
+        sphx::StepScalars h;
+        if (int rc = readScalars(w, static_cast<cudaStream_t>(a->stream), h)) return rc;
         fillResult(h, a->p, r);
         return errFlagsToStatus(h.errFlags);
     }

@@ -149,6 +149,14 @@ class HydroData:
         a = self.args()
         _cabi.check(self.L.sphx_find_neighbors_xmass(C.byref(a), C.byref(self.result) if sync else None))
 
+    def find_neighbors_sph(self, sync=True):
+        a = self.args()
+        _cabi.check(self.L.sphx_find_neighbors_sph(C.byref(a), C.byref(self.result) if sync else None))
+
+    def xmass(self):
+        a = self.args()
+        _cabi.check(self.L.sphx_xmass(C.byref(a)))
+
     def ve_def_gradh(self):
         a = self.args()
         _cabi.check(self.L.sphx_ve_def_gradh(C.byref(a)))
