@@ -24,37 +24,43 @@
 #include "sphx_block.cuh"
 #include "sphx_kernels.h"
 
+#include <algorithm>
+
 namespace sphx
 {
 
-constexpr int kSearchThreads  = kBlockTargets;
-constexpr int kTileCap        = 768;   // staged particles per tile (incl. padding), multiple of 4
-constexpr int kMaxLeaves      = 512;   // leaves overlapping one block's bounding box
-constexpr int kMaxProvisional = 16384; // particles in those leaves (15-bit provisional index)
-constexpr int kMaxTiles       = 48;
-constexpr int kFrontierCap    = 1024; // nodes per tree level that overlap the block's bounding box
+constexpr int kSearchThreads = kBlockTargets;
+constexpr int kSearchWarps   = kSearchThreads / 32;
+constexpr int kTileCap       = 768;  // staged particles per tile (incl. padding), multiple of 4
+constexpr int kMaxLeaves     = 512;  // leaves overlapping one block's bounding box
+constexpr int kMaxWords      = 768;  // provisional numbering: 32 slots per word, every leaf starts a new word
+constexpr int kMaxTiles      = 48;
+constexpr int kFrontierCap   = 1024; // nodes per tree level that overlap the block's bounding box
+constexpr int kWordsPerThread = kMaxWords / kSearchThreads;
+static_assert(kMaxWords % kSearchThreads == 0, "prefix sum: a fixed number of words per thread");
 
 struct SearchShared
 {
     // staged particles, SoA so that four consecutive x (y, z) are one 16-byte load and pair up for the packed
     // f32x2 arithmetic; every leaf is padded to a multiple of four entries with far-away dummies
     float          tileX[kTileCap], tileY[kTileCap], tileZ[kTileCap];
-    unsigned       tileJ[kTileCap]; // particle index, ~0u for padding
-    unsigned       usedBits[kMaxProvisional / 32];
-    unsigned short wordPrefix[kMaxProvisional / 32];
+    unsigned       usedBits[kMaxWords];   // union over the block's targets of the hit masks, per provisional word
+    unsigned short wordPrefix[kMaxWords]; // number of used provisional slots before each word
+    unsigned short wordLeaf[kMaxWords];   // (sorted) leaf that owns the word
     int            leafKey[kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
     int            leafFirst[kMaxLeaves]; // first particle of the sorted leaf
-    int            leafP0[kMaxLeaves];    // provisional index of that particle
+    unsigned short leafW0[kMaxLeaves];    // first provisional word of the leaf
+    unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
     float          leafBox[kMaxLeaves * 6];
     int            tileFirstLeaf[kMaxTiles + 1];
-    unsigned char  used8[kTileCap];
-    double         red[6 * (kSearchThreads / 32)];
+    unsigned short rowWord[kSearchWarps][kMaskRows]; // provisional word of each hit-mask row of a warp
+    double         red[6 * kSearchWarps];
     int            count[2];
-    int            nLeaf, nTiles, err, pEnd;
+    int            nLeaf, nTiles, err, wEnd;
     int            maxLeafHalf[3];
-    int            scan[kSearchThreads / 32];
-    int            selfP[kSearchThreads]; // provisional index of each target's own particle
-    unsigned       candBegin, numCand;
+    int            scan[kSearchWarps];
+    int            selfP[kSearchThreads]; // provisional slot of each target's own particle
+    unsigned       candBegin, numCand, nextBlock;
 };
 
 struct SearchArgs
@@ -65,10 +71,11 @@ struct SearchArgs
     const double *x, *y, *z;
     float*        h;
     unsigned*     nc;
-    unsigned      ng0, ngmax, nkbMax;
+    unsigned      ng0, ngmax, nkbMax, numBlocks;
     uint4*        list;
     float4*       cand;
     unsigned      candCapacity;
+    unsigned*     maskScratch; // per resident CTA: kSearchWarps x kMaskRows x 32 hit-mask words
     BlockDesc*    blocks;
     StepScalars*  scal;
 };
@@ -76,9 +83,9 @@ struct SearchArgs
 size_t searchSharedBytes(unsigned) { return sizeof(SearchShared); }
 
 //! the reference's pair predicate (findneighbors.hpp:33-60,117,134), every fp64 operation rounded separately
-__device__ __forceinline__ bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
-                                          const double* __restrict__ z, unsigned j, double xi, double yi, double zi,
-                                          bool usePbc, const DevBox& box, float radiusSq)
+__device__ __noinline__ bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
+                                       const double* __restrict__ z, unsigned j, double xi, double yi, double zi,
+                                       bool usePbc, const DevBox& box, float radiusSq)
 {
     double dx = __dsub_rn(x[j], xi);
     double dy = __dsub_rn(y[j], yi);
@@ -106,49 +113,51 @@ __device__ __forceinline__ float4 relativePosition(const SearchArgs& a, unsigned
     return make_float4(float(X), float(Y), float(Z), __uint_as_float(j));
 }
 
+/*! @brief search of one block of 128 targets (one per thread)
+ *
+ * Hits are recorded as bit masks: for every 32 staged particles of a leaf ("provisional word") a thread shifts one bit
+ * per pair test into a register; when the word is complete the warp stores its 32 masks as one 128-byte row of its
+ * scratch (rows that no lane hit are dropped) and ORs them into the block's used-slot mask. Only after the h-iteration
+ * has converged are the rows decoded into the 16-bit neighbour list.
+ *
+ * @param blk      block index
+ * @param maskCol  this thread's column of its warp's hit-mask scratch (row r at maskCol[32 r])
+ */
 template<bool IterateH>
-__global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __grid_constant__ SearchArgs a)
+__device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s, const unsigned blk,
+                                            unsigned* __restrict__ maskCol)
 {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    SearchShared& s = *reinterpret_cast<SearchShared*>(smemRaw);
     // scratch of the tree walk, aliased onto arrays that are written only later:
     int* frontier = reinterpret_cast<int*>(s.tileX);    // [2][kFrontierCap]: until the first tile is staged
     int* leafNode = reinterpret_cast<int*>(s.leafBox);  // leaves in traversal order: until they are ranked
     int* leafTmp  = reinterpret_cast<int*>(s.usedBits); // node index of the ranked leaves: until the leaf boxes exist
-    static_assert(2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX) + sizeof(s.tileJ), "frontier scratch");
+    static_assert(2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX), "frontier scratch");
     static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.leafBox), "leaf scratch");
-    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.usedBits) + sizeof(s.wordPrefix), "ranked-leaf scratch");
+    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.usedBits), "ranked-leaf scratch");
     static_assert(offsetof(SearchShared, tileY) == offsetof(SearchShared, tileX) + sizeof(s.tileX) &&
-                      offsetof(SearchShared, wordPrefix) == offsetof(SearchShared, usedBits) + sizeof(s.usedBits),
+                      offsetof(SearchShared, tileZ) == offsetof(SearchShared, tileY) + sizeof(s.tileY),
                   "aliased arrays must be contiguous");
-
-
 
     constexpr int T    = kBlockTargets;
     const int     t    = threadIdx.x;
     const int     lane = t & 31, warp = t >> 5;
 
-    /* Hit columns. Provisional hits of thread t = (warp g, lane) go to row k of the group's slice of the final list
-     * storage, hitCol[k * 32] (u16, 64 bytes per row and group): L2-resident scratch instead of 38 KB of shared memory
-     * per CTA, which more than doubles the number of resident CTAs. The list writer converts the slice in place, warp
-     * synchronously: the final vector (kb, lane) covers exactly provisional rows 8 kb .. 8 kb + 7 (see there). */
-    unsigned short* const hitCol =
-        reinterpret_cast<unsigned short*>(a.list + (size_t(blockIdx.x) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize) +
-        lane;
-    const unsigned i     = a.first + blockIdx.x * T + t;
-    const bool     valid = i < a.last;
-    const unsigned il    = valid ? i : a.last - 1;
+    const unsigned iBlock0 = a.first + blk * T;
+    const unsigned i       = iBlock0 + t;
+    const bool     valid   = i < a.last;
+    const unsigned il      = valid ? i : a.last - 1;
     const double   xi = a.x[il], yi = a.y[il], zi = a.z[il];
     float          hi        = a.h[il];
     bool           hChanged  = false;
     int            iteration = 0;
     unsigned       count     = 0;
+    unsigned       numRows   = 0; // hit-mask rows of this warp (warp-uniform)
     const unsigned ngmax     = a.ngmax;
     const DevBox&  box       = a.box;
 
     double ox = 0, oy = 0, oz = 0;
     bool   foldMode = false;
-    int    L = 0, pEnd = 0;
+    int    L = 0;
 
     for (;;)
     {
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
         for (int d = 0; d < 3; ++d)
         {
             lo[d] = s.red[d], up[d] = s.red[3 + d];
-            for (int w = 1; w < kSearchThreads / 32; ++w)
+            for (int w = 1; w < kSearchWarps; ++w)
             {
                 lo[d] = fmin(lo[d], s.red[w * 6 + d]);
                 up[d] = fmax(up[d], s.red[w * 6 + 3 + d]);
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
             int       rk  = 0;
             for (int m = 0; m < L; ++m)
                 rk += s.leafKey[m] < key;
-            leafTmp[rk]   = leafNode[q];
+            leafTmp[rk]     = leafNode[q];
             s.leafFirst[rk] = key;
         }
         __syncthreads();
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
         }
         const float E = __double2float_ru(fmax(ex, fmax(ey, ez))) * 1.0001f;
 
-        // leaf boxes relative to the block origin (for the per-warp cull), provisional numbering, tiles
+        // leaf boxes relative to the block origin (for the per-warp cull)
         for (int q = t; q < L; q += T)
         {
             const int node = leafTmp[q];
@@ -321,18 +330,20 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
             s.leafBox[q * 6 + 4] = __double2float_ru(a.tree.sizes[3 * node + 1]) * 1.00001f + slop;
             s.leafBox[q * 6 + 5] = __double2float_ru(a.tree.sizes[3 * node + 2]) * 1.00001f + slop;
         }
+        __syncthreads(); // leafTmp (aliased onto usedBits) is dead from here on
+
+        // provisional numbering (every leaf starts a new 32-slot word), tiles; meanwhile everybody clears the used mask
         if (t == 0)
         {
-            int P = 0, nT = 0, tileCount = 0, err = 0;
+            int W = 0, nT = 0, tileCount = 0, err = 0;
             s.tileFirstLeaf[0] = 0;
-#pragma unroll 4
             for (int q = 0; q < L; ++q)
             {
-                const int c = (s.leafKey[q] + 3) & ~3; // padded to a multiple of four
+                const int n = s.leafKey[q];
+                const int c = (n + 3) & ~3; // padded to a multiple of four
                 if (c > kTileCap) err = 1;
                 if (tileCount + c > kTileCap)
                 {
-                    P = (P + 31) & ~31;
                     ++nT;
                     if (nT >= kMaxTiles)
                     {
@@ -342,20 +353,30 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
                     s.tileFirstLeaf[nT] = q;
                     tileCount           = 0;
                 }
-                s.leafP0[q] = P;
-                P += c;
+                const int nw = (n + 31) >> 5;
+                if (W + nw > kMaxWords || err)
+                {
+                    err = 1;
+                    break;
+                }
+                s.leafTile[q] = (unsigned short)tileCount;
+                s.leafW0[q]   = (unsigned short)W;
+                for (int k = 0; k < nw; ++k)
+                    s.wordLeaf[W + k] = (unsigned short)q;
+                W += nw;
                 tileCount += c;
             }
             ++nT;
             s.tileFirstLeaf[nT] = L;
             s.nTiles            = nT;
-            s.pEnd              = P;
-            if (P > kMaxProvisional) err = 1;
+            s.wEnd              = W;
             if (err) s.err = 1;
         }
+#pragma unroll
+        for (int q = 0; q < kWordsPerThread; ++q)
+            s.usedBits[q * T + t] = 0;
         __syncthreads();
         if (s.err) break;
-        pEnd             = s.pEnd;
         const int nTiles = s.nTiles;
 
         // ---------------------------------------------------------------------------------------------------------
@@ -371,41 +392,40 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
             r2hi               = foldMode ? 3.0e38f : radiusSq + margin;
             if (!valid) r2lo = r2hi = -1.0f;
         }
+        /* e = d2 - r2lo: the sign bit of e is the sure-hit decision (IEEE subtraction has the exact sign); a pair is
+         * ambiguous when 0 <= e < r2hi - r2lo, tested on the bit patterns (unsigned order == float order for e >= 0,
+         * negative e compare as huge). The width is inflated so that rounding of e cannot hide a d2 < r2hi. */
+        const float2   nlo2      = make_float2(-r2lo, -r2lo);
+        const unsigned widthBits = __float_as_uint((r2hi - r2lo) * 1.0001f);
 
-        unsigned       slot    = 0;                     // next free element of this thread's hit column (row * 32)
-        const unsigned slotEnd = (ngmax + 1) * kGroupSize; // the column also receives the target's own particle
-        const unsigned iBlock0 = a.first + blockIdx.x * T;
+        unsigned row = 0;
+        count        = 0;
         for (int tIdx = 0; tIdx < nTiles; ++tIdx)
         {
             const int lb = s.tileFirstLeaf[tIdx], le = s.tileFirstLeaf[tIdx + 1];
             if (lb == le) continue;
-            const int tileBase = s.leafP0[lb];
-            const int tileN    = s.leafP0[le - 1] + ((s.leafKey[le - 1] + 3) & ~3) - tileBase;
+            const int tileN = s.leafTile[le - 1] + ((s.leafKey[le - 1] + 3) & ~3);
 
             // stage
             {
                 int l = lb;
                 for (int p = t; p < tileN; p += T)
                 {
-                    const int P = tileBase + p;
-                    while (P >= s.leafP0[l] + ((s.leafKey[l] + 3) & ~3))
+                    while (p >= s.leafTile[l] + ((s.leafKey[l] + 3) & ~3))
                         ++l;
-                    const int off = P - s.leafP0[l];
-                    float4    rp  = make_float4(1e18f, 1e18f, 1e18f, __uint_as_float(~0u)); // padding: never a hit
+                    const int off = p - s.leafTile[l];
+                    float4    rp  = make_float4(1e18f, 1e18f, 1e18f, 0.0f); // padding: never a hit
                     if (off < s.leafKey[l])
                     {
                         const unsigned j = unsigned(s.leafFirst[l] + off);
                         rp               = relativePosition(a, j, ox, oy, oz, foldMode);
-                        if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = P;
+                        if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = 32 * int(s.leafW0[l]) + off;
                     }
                     s.tileX[p] = rp.x, s.tileY[p] = rp.y, s.tileZ[p] = rp.z;
-                    s.tileJ[p] = __float_as_uint(rp.w);
-                    s.used8[p] = 0;
                 }
             }
             __syncthreads();
 
-            const unsigned slotTile = slot;
             for (int l = lb; l < le; ++l)
             {
                 // does any sphere of this warp touch the leaf?
@@ -416,74 +436,78 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
                 const bool   touch = ddx * ddx + ddy * ddy + ddz * ddz <= r2hi;
                 if (!__any_sync(kFullMask, touch)) continue;
 
-                const int pb = s.leafP0[l] - tileBase;
-                const int pe = pb + s.leafKey[l];
-                // four staged particles per step in straight-line code; distances in packed f32x2 arithmetic
-                for (int p = pb; p < pe; p += 4)
+                const int n  = s.leafKey[l];
+                const int pb = s.leafTile[l];
+                unsigned  w  = s.leafW0[l];
+                for (int c0 = 0; c0 < n; c0 += 32, ++w)
                 {
-                    const float4 X = *reinterpret_cast<const float4*>(&s.tileX[p]);
-                    const float4 Y = *reinterpret_cast<const float4*>(&s.tileY[p]);
-                    const float4 Z = *reinterpret_cast<const float4*>(&s.tileZ[p]);
-                    const float2 dx0 = __fadd2_rn(make_float2(X.x, X.y), ntx), dx1 = __fadd2_rn(make_float2(X.z, X.w), ntx);
-                    const float2 dy0 = __fadd2_rn(make_float2(Y.x, Y.y), nty), dy1 = __fadd2_rn(make_float2(Y.z, Y.w), nty);
-                    const float2 dz0 = __fadd2_rn(make_float2(Z.x, Z.y), ntz), dz1 = __fadd2_rn(make_float2(Z.z, Z.w), ntz);
-                    const float2 s0 = __ffma2_rn(dz0, dz0, __ffma2_rn(dy0, dy0, __fmul2_rn(dx0, dx0)));
-                    const float2 s1 = __ffma2_rn(dz1, dz1, __ffma2_rn(dy1, dy1, __fmul2_rn(dx1, dx1)));
-                    const float  d2[4] = {s0.x, s0.y, s1.x, s1.y};
-                    // a pair is a sure hit below r2lo and a sure miss from r2hi on; in between (or in fold mode) the
-                    // reference's exact fp64 predicate decides. The target's own particle (d2 = 0) is recorded like
-                    // any other hit and dropped when the list is written.
-                    bool amb = false;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        amb = amb | (!(d2[u] < r2lo) & (d2[u] < r2hi));
-                    if (__any_sync(kFullMask, amb))
+                    // up to eight quads of staged particles = one provisional word; distances in packed f32x2 arithmetic
+                    const int     nq = min(8, (n - c0 + 3) >> 2);
+                    const float4* px = reinterpret_cast<const float4*>(&s.tileX[pb + c0]);
+                    const float4* py = reinterpret_cast<const float4*>(&s.tileY[pb + c0]);
+                    const float4* pz = reinterpret_cast<const float4*>(&s.tileZ[pb + c0]);
+                    unsigned      mask = 0;
+#pragma unroll 2
+                    for (int q = 0; q < nq; ++q)
                     {
+                        const float4 X = px[q], Y = py[q], Z = pz[q];
+                        const float2 dx0 = __fadd2_rn(make_float2(X.x, X.y), ntx), dx1 = __fadd2_rn(make_float2(X.z, X.w), ntx);
+                        const float2 dy0 = __fadd2_rn(make_float2(Y.x, Y.y), nty), dy1 = __fadd2_rn(make_float2(Y.z, Y.w), nty);
+                        const float2 dz0 = __fadd2_rn(make_float2(Z.x, Z.y), ntz), dz1 = __fadd2_rn(make_float2(Z.z, Z.w), ntz);
+                        const float2 s0 = __ffma2_rn(dz0, dz0, __ffma2_rn(dy0, dy0, __fmul2_rn(dx0, dx0)));
+                        const float2 s1 = __ffma2_rn(dz1, dz1, __ffma2_rn(dy1, dy1, __fmul2_rn(dx1, dx1)));
+                        const float2 e0 = __fadd2_rn(s0, nlo2), e1 = __fadd2_rn(s1, nlo2);
+                        const unsigned eb[4] = {__float_as_uint(e0.x), __float_as_uint(e0.y), __float_as_uint(e1.x),
+                                                __float_as_uint(e1.y)};
+                        const bool amb = (eb[0] < widthBits) | (eb[1] < widthBits) | (eb[2] < widthBits) |
+                                         (eb[3] < widthBits);
+                        if (__any_sync(kFullMask, amb))
+                        {
+                            // the reference's exact fp64 predicate decides inside the margin (and always in fold mode)
+                            const float d2[4] = {s0.x, s0.y, s1.x, s1.y};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                bool h = eb[u] >> 31;
+                                if (!h && d2[u] < r2hi)
+                                {
+                                    const int off = c0 + 4 * q + u;
+                                    h = off < n && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), xi, yi, zi,
+                                                             usePbc, box, radiusSq);
+                                }
+                                mask = (mask << 1) | unsigned(h);
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
+                            mask = __funnelshift_l(eb[u], mask, 1); // (mask << 1) | sign(e)
+                    }
+                    mask <<= 32 - 4 * nq; // staged particle c0 + k of the leaf is bit 31 - k
+                    const unsigned any = __reduce_or_sync(kFullMask, mask);
+                    if (any)
+                    {
+                        count += __popc(mask);
+                        if (row < kMaskRows)
                         {
-                            bool h = d2[u] < r2hi;
-                            if (h && !(d2[u] < r2lo))
+                            maskCol[row * 32] = mask;
+                            if (lane == 0)
                             {
-                                const unsigned j = s.tileJ[p + u];
-                                h = j != ~0u && exactPair(a.x, a.y, a.z, j, xi, yi, zi, usePbc, box, radiusSq);
-                            }
-                            if (h)
-                            {
-                                if (slot < slotEnd) hitCol[slot] = (unsigned short)(tileBase + p + u);
-                                slot += kGroupSize;
+                                s.rowWord[warp][row] = (unsigned short)w;
+                                atomicOr(&s.usedBits[w], any);
                             }
                         }
-                        continue;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                    {
-                        const bool hit = d2[u] < r2lo;
-                        if (hit && slot < slotEnd) hitCol[slot] = (unsigned short)(tileBase + p + u);
-                        slot += hit ? kGroupSize : 0u;
+                        else { s.err = 1; }
+                        ++row;
                     }
                 }
             }
-
-            // mark the staged particles this thread kept
-            {
-                const unsigned kEnd = min(slot, slotEnd);
-                for (unsigned k = slotTile; k < kEnd; k += kGroupSize)
-                    s.used8[hitCol[k] - tileBase] = 1;
-            }
-            __syncthreads();
-            for (int base = warp * 32; base < tileN; base += kSearchThreads)
-            {
-                const bool     bit = (base + lane < tileN) && s.used8[base + lane];
-                const unsigned m   = __ballot_sync(kFullMask, bit);
-                if (lane == 0) s.usedBits[(tileBase + base) >> 5] = m;
-            }
-            __syncthreads();
+            __syncthreads(); // all reads of the tile are done
         }
+        numRows = row;
+        if (s.err) break;
 
         // number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
-        count = slot / kGroupSize;
         if (valid && s.selfP[t] >= 0 && count > 0) --count;
 
         // ---------------------------------------------------------------------------------------------------------
@@ -515,20 +539,20 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
         {
             atomicOr(&a.scal->errFlags, kErrTraversal);
             desc.candBegin = 0, desc.numCand = 0;
-            a.blocks[blockIdx.x] = desc;
+            a.blocks[blk] = desc;
         }
         if (valid) a.nc[i] = 1;
         return;
     }
 
-    // popc prefix over the used-bit words -> compact candidate numbering
+    // popc prefix over the used-slot words -> compact candidate numbering
+    const int nW = s.wEnd;
     {
-        const int nW  = (pEnd + 31) >> 5;
-        const int w0  = t * 8;
-        int       loc[8];
+        const int w0 = t * kWordsPerThread;
+        int       loc[kWordsPerThread];
         int       sum = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < kWordsPerThread; ++q)
         {
             loc[q] = sum;
             sum += (w0 + q < nW) ? __popc(s.usedBits[w0 + q]) : 0;
@@ -543,84 +567,85 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
         if (lane == 31) s.scan[warp] = incl;
         __syncthreads();
         int base = 0, total = 0;
-        for (int w = 0; w < kSearchThreads / 32; ++w)
+        for (int w = 0; w < kSearchWarps; ++w)
         {
             if (w < warp) base += s.scan[w];
             total += s.scan[w];
         }
         base += incl - sum;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < kWordsPerThread; ++q)
             if (w0 + q < nW) s.wordPrefix[w0 + q] = (unsigned short)(base + loc[q]);
         if (t == 0)
         {
             unsigned begin = atomicAdd(&a.scal->candTop, unsigned(total));
             unsigned num   = unsigned(total);
-            if (size_t(begin) + num > a.candCapacity)
+            if (size_t(begin) + num > a.candCapacity || num > 0xffffu)
             {
                 atomicOr(&a.scal->errFlags, kErrCandSpace);
                 begin = 0, num = 0;
             }
             s.candBegin = begin, s.numCand = num;
             desc.candBegin = begin, desc.numCand = num;
-            a.blocks[blockIdx.x] = desc;
+            a.blocks[blk] = desc;
         }
         __syncthreads();
     }
     const unsigned candBegin = s.candBegin;
-    const bool     haveSpace = s.numCand > 0 || pEnd == 0;
+    const unsigned numCand   = s.numCand;
+    const bool     haveSpace = numCand > 0 || nW == 0;
 
-    // compacted candidate records
-    if (haveSpace)
+    // compacted candidate records, one thread per record: locate the c-th used slot (word by binary search over the
+    // prefix, then the bit), so that the fp64 position loads of different records are independent
+    for (unsigned c = t; c < numCand; c += T)
     {
-        int l = 0;
-        for (int P = t; P < pEnd; P += T)
+        int lo = 0, up = nW;
+        while (up - lo > 1)
         {
-            while (l < L && P >= s.leafP0[l] + ((s.leafKey[l] + 3) & ~3))
-                ++l;
-            if (l >= L) break;
-            if (P < s.leafP0[l]) continue; // alignment gap between tiles
-            const unsigned w = s.usedBits[P >> 5];
-            if (!((w >> (P & 31)) & 1u)) continue;
-            const unsigned c = s.wordPrefix[P >> 5] + __popc(w & ((1u << (P & 31)) - 1u));
-            const unsigned j = unsigned(s.leafFirst[l] + (P - s.leafP0[l]));
-            a.cand[size_t(candBegin) + c] = relativePosition(a, j, ox, oy, oz, foldMode);
+            const int mid = (lo + up) >> 1;
+            if (s.wordPrefix[mid] <= c) { lo = mid; }
+            else { up = mid; }
         }
+        unsigned m = s.usedBits[lo];
+        for (unsigned r = c - s.wordPrefix[lo]; r > 0; --r)
+            m &= ~(0x80000000u >> __clz(m));
+        const int      l = s.wordLeaf[lo];
+        const unsigned j = unsigned(s.leafFirst[l]) + 32u * unsigned(lo - int(s.leafW0[l])) + unsigned(__clz(m));
+        a.cand[size_t(candBegin) + c] = relativePosition(a, j, ox, oy, oz, foldMode);
     }
 
-    // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets
+    // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets. Every lane
+    // decodes its own mask column (rows with no bit for this lane are skipped), ascending, without its own particle.
     {
-        /* In-place, warp-synchronous: provisional row k of the group occupies bytes [64 k, 64 k + 64) of its slice,
-         * the final vector (kb, lane) bytes [512 kb + 16 lane, + 16), i.e. a piece of provisional row 8 kb + lane / 4.
-         * All lanes first read their rows 8 kb .. 8 kb + 8 (one extra when the own particle has been skipped), then
-         * all lanes write their vector kb, which only destroys rows 8 kb .. 8 kb + 7 that every lane has consumed. */
-        const unsigned kc     = haveSpace ? min(count, ngmax) : 0u;
-        const unsigned nkb    = (kc + 7) / 8;
-        const unsigned nkbW   = warpMaxU(nkb);
-        const unsigned selfPu = unsigned(s.selfP[t]); // provisional index of the target itself
-        unsigned       rk     = 0;                    // read cursor (row) in the hit column
-        uint4* lp = a.list + (size_t(blockIdx.x) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
-        for (unsigned kb = 0; kb < nkbW; ++kb)
+        const unsigned        kc     = haveSpace ? min(count, ngmax) : 0u;
+        const unsigned        selfPu = unsigned(s.selfP[t]);
+        const unsigned short* rw     = s.rowWord[warp];
+        uint4* lp = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
+        unsigned           r = 0, mask = 0, w = 0, k = 0;
+        unsigned long long vlo = 0, vhi = 0;
+        while (k < kc)
         {
-            unsigned wds[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
+            while (mask == 0 && r < numRows)
             {
-                const unsigned k = kb * 8 + q;
-                unsigned       e = 0;
-                if (k < kc)
-                {
-                    unsigned P = hitCol[rk * kGroupSize];
-                    if (P == selfPu) P = hitCol[++rk * kGroupSize];
-                    ++rk;
-                    const unsigned w = s.usedBits[P >> 5];
-                    e                = s.wordPrefix[P >> 5] + __popc(w & ((1u << (P & 31)) - 1u));
-                }
-                wds[q >> 1] |= e << (16 * (q & 1));
+                mask = maskCol[r * 32];
+                w    = rw[r];
+                ++r;
             }
-            __syncwarp();
-            if (kb < nkb) lp[size_t(kb) * kGroupSize] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-            __syncwarp();
+            if (mask == 0) break; // cannot happen: count bits were recorded
+            const unsigned b = __clz(mask);
+            mask &= ~(0x80000000u >> b);
+            if (32u * w + b == selfPu) continue;
+            const unsigned e = s.wordPrefix[w] + __popc(s.usedBits[w] & ~(0xffffffffu >> b));
+            const unsigned long long ev = (unsigned long long)(e) << (16 * (k & 3));
+            if (k & 4) { vhi |= ev; }
+            else { vlo |= ev; }
+            ++k;
+            if ((k & 7) == 0 || k == kc)
+            {
+                lp[size_t((k - 1) >> 3) * kGroupSize] =
+                    make_uint4(unsigned(vlo), unsigned(vlo >> 32), unsigned(vhi), unsigned(vhi >> 32));
+                vlo = vhi = 0;
+            }
         }
     }
 
@@ -649,6 +674,25 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
     {
         if (hChanged) a.h[i] = hi;
         a.nc[i] = ncSph;
+    }
+}
+
+//! persistent CTAs take blocks of 128 targets from a work counter; each CTA owns one slice of the hit-mask scratch
+template<bool IterateH>
+__global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __grid_constant__ SearchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SearchShared&   s = *reinterpret_cast<SearchShared*>(smemRaw);
+    unsigned* const maskCol =
+        a.maskScratch + (size_t(blockIdx.x) * kSearchWarps + (threadIdx.x >> 5)) * kMaskRows * 32 + (threadIdx.x & 31);
+    for (;;)
+    {
+        __syncthreads(); // the previous block's shared-memory state is dead
+        if (threadIdx.x == 0) s.nextBlock = atomicAdd(&a.scal->work[kSearchWork], 1u);
+        __syncthreads();
+        const unsigned blk = s.nextBlock;
+        if (blk >= a.numBlocks) break;
+        searchBlock<IterateH>(a, s, blk, maskCol);
     }
 }
 
@@ -692,6 +736,32 @@ static cudaError_t configureSearch(unsigned ngmax)
     return cudaSuccess;
 }
 
+static int smCountSearch()
+{
+    static int n = 0;
+    if (n == 0)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+//! resident CTAs per SM of the search kernel (occupancy query, cached)
+static int searchCtasPerSm()
+{
+    static int n = 0;
+    if (n == 0)
+    {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blockSearchKernel<true>, kSearchThreads,
+                                                      searchSharedBytes(0));
+        if (n <= 0) n = 1;
+    }
+    return n;
+}
+
 cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t stream)
 {
     unsigned n = unsigned(a.last - a.first);
@@ -704,13 +774,15 @@ cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, c
     s.box  = makeDevBox(a.box);
     s.tree = a.tree;
     s.x = a.f.x, s.y = a.f.y, s.z = a.f.z, s.h = a.f.h, s.nc = a.f.nc;
-    s.ng0 = a.p.ng0, s.ngmax = a.p.ngmax, s.nkbMax = w.nkbMax;
+    s.ng0 = a.p.ng0, s.ngmax = a.p.ngmax, s.nkbMax = w.nkbMax, s.numBlocks = w.numBlocks;
+    s.maskScratch  = reinterpret_cast<unsigned*>(base + w.maskOff);
     s.list         = reinterpret_cast<uint4*>(base + w.listOff);
     s.cand         = reinterpret_cast<float4*>(base + w.candOff);
     s.candCapacity = unsigned(w.candCapacity > 0xffffffffull ? 0xffffffffull : w.candCapacity);
     s.blocks       = reinterpret_cast<BlockDesc*>(base + w.blocksOff);
     s.scal         = reinterpret_cast<StepScalars*>(base + w.scalOff);
-    blockSearchKernel<true><<<w.numBlocks, kSearchThreads, searchSharedBytes(a.p.ngmax), stream>>>(s);
+    unsigned grid = std::min(std::min(w.numBlocks, kSearchMaxCtas), unsigned(searchCtasPerSm() * smCountSearch()));
+    blockSearchKernel<true><<<grid, kSearchThreads, searchSharedBytes(a.p.ngmax), stream>>>(s);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,10 @@ namespace sphx
 constexpr int      kBlockTargets   = 128; // targets per block (T)
 constexpr int      kGroupsPerBlock = kBlockTargets / int(kGroupSize);
 constexpr unsigned kCandPerTarget  = 16;  // candidate-array capacity per assigned particle (typical use: 8-10)
-constexpr unsigned kMaxNgmaxStep   = 384; // the hit buffer of the block search lives in shared memory
+constexpr unsigned kMaxNgmaxStep   = 384; // list vectors per target: (ngmax + 8) / 8 <= 49
+constexpr unsigned kMaskRows       = 128; // hit-mask rows (32 staged particles each) per warp of the block search
+constexpr unsigned kSearchMaxCtas  = 1024; // resident CTAs of the persistent block search (each owns a scratch slice)
+constexpr int      kSearchWork     = 5;   // StepScalars::work slot of the block search (0..4: the loop kernels)
 
 constexpr unsigned kBlockFold = 1u; // BlockDesc::flags: fold mode
 
@@ -54,7 +57,7 @@ __host__ __device__ inline size_t   alignUp(size_t v, size_t a) { return (v + a 
 //! workspace carving, shared by api.cu and the kernels' launchers
 struct WorkspaceLayout
 {
-    size_t   scalOff, blocksOff, listOff, candOff, total;
+    size_t   scalOff, blocksOff, listOff, candOff, maskOff, total;
     unsigned numBlocks, nkbMax;
     size_t   candCapacity;
 
@@ -67,7 +70,10 @@ struct WorkspaceLayout
         blocksOff    = kScalarsBytes;
         listOff      = alignUp(blocksOff + size_t(numBlocks) * sizeof(BlockDesc), 256);
         candOff      = alignUp(listOff + size_t(numBlocks) * kGroupsPerBlock * nkbMax * kGroupSize * 16, 256);
-        total        = alignUp(candOff + candCapacity * 16, 256);
+        maskOff      = alignUp(candOff + candCapacity * 16, 256);
+        // hit-mask scratch of the block search: one slice per resident CTA, L2-resident (written and read once per block)
+        size_t ctas  = numBlocks < kSearchMaxCtas ? numBlocks : kSearchMaxCtas;
+        total        = alignUp(maskOff + ctas * kBlockTargets * kMaskRows * sizeof(unsigned), 256);
     }
 };
 
