@@ -53,7 +53,6 @@ struct SearchShared
     unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
     float          leafBox[kMaxLeaves * 6];
     int            tileFirstLeaf[kMaxTiles + 1];
-    unsigned short rowWord[kSearchWarps][kMaskRows]; // provisional word of each hit-mask row of a warp
     double         red[6 * kSearchWarps];
     int            count[2];
     int            nLeaf, nTiles, err, wEnd;
@@ -75,7 +74,7 @@ struct SearchArgs
     uint4*        list;
     float4*       cand;
     unsigned      candCapacity;
-    unsigned*     maskScratch; // per resident CTA: kSearchWarps x kMaskRows x 32 hit-mask words
+    uint2*        maskScratch; // per resident CTA: kBlockTargets columns of kMaskRows {hit mask, provisional word}
     BlockDesc*    blocks;
     StepScalars*  scal;
 };
@@ -116,16 +115,16 @@ __device__ __forceinline__ float4 relativePosition(const SearchArgs& a, unsigned
 /*! @brief search of one block of 128 targets (one per thread)
  *
  * Hits are recorded as bit masks: for every 32 staged particles of a leaf ("provisional word") a thread shifts one bit
- * per pair test into a register; when the word is complete the warp stores its 32 masks as one 128-byte row of its
- * scratch (rows that no lane hit are dropped) and ORs them into the block's used-slot mask. Only after the h-iteration
- * has converged are the rows decoded into the 16-bit neighbour list.
+ * per pair test into a register; when the word is complete, a thread with at least one hit appends {mask, word} to its
+ * private column of the L2-resident scratch and the warp ORs its masks into the block's used-slot mask. Only after the
+ * h-iteration has converged are the columns decoded into the 16-bit neighbour list.
  *
  * @param blk      block index
- * @param maskCol  this thread's column of its warp's hit-mask scratch (row r at maskCol[32 r])
+ * @param maskCol  this thread's column of the hit-mask scratch (entry r at maskCol[32 r])
  */
 template<bool IterateH>
 __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s, const unsigned blk,
-                                            unsigned* __restrict__ maskCol)
+                                            uint2* __restrict__ maskCol)
 {
     // scratch of the tree walk, aliased onto arrays that are written only later:
     int* frontier = reinterpret_cast<int*>(s.tileX);    // [2][kFrontierCap]: until the first tile is staged
@@ -151,7 +150,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     bool           hChanged  = false;
     int            iteration = 0;
     unsigned       count     = 0;
-    unsigned       numRows   = 0; // hit-mask rows of this warp (warp-uniform)
+    unsigned       numEnt    = 0; // entries in this thread's hit-mask column
     const unsigned ngmax     = a.ngmax;
     const DevBox&  box       = a.box;
 
@@ -398,8 +397,10 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         const float2   nlo2      = make_float2(-r2lo, -r2lo);
         const unsigned widthBits = __float_as_uint((r2hi - r2lo) * 1.0001f);
 
-        unsigned row = 0;
-        count        = 0;
+        unsigned ent   = 0;
+        int      selfW = -1;          // provisional word and bit of the target's own particle, once it has been staged
+        unsigned selfClear = ~0u;
+        count              = 0;
         for (int tIdx = 0; tIdx < nTiles; ++tIdx)
         {
             const int lb = s.tileFirstLeaf[tIdx], le = s.tileFirstLeaf[tIdx + 1];
@@ -425,6 +426,11 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                 }
             }
             __syncthreads();
+            {
+                const int sp = s.selfP[t];
+                selfW        = sp >> 5; // negative while unknown
+                selfClear    = ~(0x80000000u >> (sp & 31));
+            }
 
             for (int l = lb; l < le; ++l)
             {
@@ -484,31 +490,23 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                             mask = __funnelshift_l(eb[u], mask, 1); // (mask << 1) | sign(e)
                     }
                     mask <<= 32 - 4 * nq; // staged particle c0 + k of the leaf is bit 31 - k
+                    if (int(w) == selfW) mask &= selfClear; // the target itself is not a neighbour
                     const unsigned any = __reduce_or_sync(kFullMask, mask);
-                    if (any)
+                    if (any && lane == 0) atomicOr(&s.usedBits[w], any);
+                    if (mask)
                     {
                         count += __popc(mask);
-                        if (row < kMaskRows)
-                        {
-                            maskCol[row * 32] = mask;
-                            if (lane == 0)
-                            {
-                                s.rowWord[warp][row] = (unsigned short)w;
-                                atomicOr(&s.usedBits[w], any);
-                            }
-                        }
+                        if (ent < kMaskRows) { maskCol[ent * 32] = make_uint2(mask, w); }
                         else { s.err = 1; }
-                        ++row;
+                        ++ent;
                     }
                 }
             }
             __syncthreads(); // all reads of the tile are done
         }
-        numRows = row;
+        numEnt = ent;
         if (s.err) break;
-
-        // number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
-        if (valid && s.selfP[t] >= 0 && count > 0) --count;
+        // count = number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
 
         // ---------------------------------------------------------------------------------------------------------
         // sph/find_neighbors.hpp:17-36: while ((ngmin > nc || nc - 1 > ngmax) && iteration++ < 10)
@@ -546,7 +544,8 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     }
 
     // popc prefix over the used-slot words -> compact candidate numbering
-    const int nW = s.wEnd;
+    const int nW    = s.wEnd;
+    int       total = 0;
     {
         const int w0 = t * kWordsPerThread;
         int       loc[kWordsPerThread];
@@ -566,7 +565,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         }
         if (lane == 31) s.scan[warp] = incl;
         __syncthreads();
-        int base = 0, total = 0;
+        int base = 0;
         for (int w = 0; w < kSearchWarps; ++w)
         {
             if (w < warp) base += s.scan[w];
@@ -576,10 +575,57 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
 #pragma unroll
         for (int q = 0; q < kWordsPerThread; ++q)
             if (w0 + q < nW) s.wordPrefix[w0 + q] = (unsigned short)(base + loc[q]);
+        unsigned begin = 0;
+        if (t == 0) begin = atomicAdd(&a.scal->candTop, unsigned(total)); // consumed after the list decode
+        __syncthreads(); // wordPrefix complete
+
+        // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets. Every lane
+        // decodes its own mask column at its own pace (one neighbour per iteration, next entry prefetched), ascending.
+        {
+            const unsigned kc = min(count, ngmax);
+            uint4* lp = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
+            uint2  cur = make_uint2(0u, 0u), nxt = cur;
+            if (numEnt > 0) cur = maskCol[0];
+            if (numEnt > 1) nxt = maskCol[32];
+            unsigned r    = 2;
+            unsigned mask = cur.x, w = cur.y;
+            cur           = nxt;
+            nxt           = make_uint2(0u, 0u);
+            if (r < numEnt) nxt = maskCol[r * 32];
+            ++r;
+            unsigned           ub = s.usedBits[w], pre = s.wordPrefix[w];
+            unsigned long long vlo = 0, vhi = 0;
+            unsigned           k   = 0;
+            while (k < kc && mask)
+            {
+                const unsigned b = __clz(mask);
+                mask &= ~(0x80000000u >> b);
+                const unsigned           e  = pre + __popc(ub & ~(0xffffffffu >> b));
+                const unsigned long long ev = (unsigned long long)(e) << (16 * (k & 3));
+                if (k & 4) { vhi |= ev; }
+                else { vlo |= ev; }
+                ++k;
+                if ((k & 7) == 0 || k == kc)
+                {
+                    lp[size_t((k - 1) >> 3) * kGroupSize] =
+                        make_uint4(unsigned(vlo), unsigned(vlo >> 32), unsigned(vhi), unsigned(vhi >> 32));
+                    vlo = vhi = 0;
+                }
+                if (mask == 0)
+                {
+                    mask = cur.x, w = cur.y;
+                    cur = nxt;
+                    nxt = make_uint2(0u, 0u);
+                    if (r < numEnt) nxt = maskCol[r * 32];
+                    ++r;
+                    ub = s.usedBits[w], pre = s.wordPrefix[w];
+                }
+            }
+        }
+
         if (t == 0)
         {
-            unsigned begin = atomicAdd(&a.scal->candTop, unsigned(total));
-            unsigned num   = unsigned(total);
+            unsigned num = unsigned(total);
             if (size_t(begin) + num > a.candCapacity || num > 0xffffu)
             {
                 atomicOr(&a.scal->errFlags, kErrCandSpace);
@@ -593,7 +639,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     }
     const unsigned candBegin = s.candBegin;
     const unsigned numCand   = s.numCand;
-    const bool     haveSpace = numCand > 0 || nW == 0;
+    const bool     haveSpace = numCand == unsigned(total);
 
     // compacted candidate records, one thread per record: locate the c-th used slot (word by binary search over the
     // prefix, then the bit), so that the fp64 position loads of different records are independent
@@ -612,41 +658,6 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         const int      l = s.wordLeaf[lo];
         const unsigned j = unsigned(s.leafFirst[l]) + 32u * unsigned(lo - int(s.leafW0[l])) + unsigned(__clz(m));
         a.cand[size_t(candBegin) + c] = relativePosition(a, j, ox, oy, oz, foldMode);
-    }
-
-    // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets. Every lane
-    // decodes its own mask column (rows with no bit for this lane are skipped), ascending, without its own particle.
-    {
-        const unsigned        kc     = haveSpace ? min(count, ngmax) : 0u;
-        const unsigned        selfPu = unsigned(s.selfP[t]);
-        const unsigned short* rw     = s.rowWord[warp];
-        uint4* lp = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
-        unsigned           r = 0, mask = 0, w = 0, k = 0;
-        unsigned long long vlo = 0, vhi = 0;
-        while (k < kc)
-        {
-            while (mask == 0 && r < numRows)
-            {
-                mask = maskCol[r * 32];
-                w    = rw[r];
-                ++r;
-            }
-            if (mask == 0) break; // cannot happen: count bits were recorded
-            const unsigned b = __clz(mask);
-            mask &= ~(0x80000000u >> b);
-            if (32u * w + b == selfPu) continue;
-            const unsigned e = s.wordPrefix[w] + __popc(s.usedBits[w] & ~(0xffffffffu >> b));
-            const unsigned long long ev = (unsigned long long)(e) << (16 * (k & 3));
-            if (k & 4) { vhi |= ev; }
-            else { vlo |= ev; }
-            ++k;
-            if ((k & 7) == 0 || k == kc)
-            {
-                lp[size_t((k - 1) >> 3) * kGroupSize] =
-                    make_uint4(unsigned(vlo), unsigned(vlo >> 32), unsigned(vhi), unsigned(vhi >> 32));
-                vlo = vhi = 0;
-            }
-        }
     }
 
     // outputs and statistics (conserved_quantities.hpp:146-157 sums nc)
@@ -673,7 +684,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     if (valid)
     {
         if (hChanged) a.h[i] = hi;
-        a.nc[i] = ncSph;
+        a.nc[i] = haveSpace ? ncSph : 1u; // candidate array exhausted (error flagged): the loops skip the block
     }
 }
 
@@ -683,16 +694,18 @@ __global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __g
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SearchShared&   s = *reinterpret_cast<SearchShared*>(smemRaw);
-    unsigned* const maskCol =
+    uint2* const maskCol =
         a.maskScratch + (size_t(blockIdx.x) * kSearchWarps + (threadIdx.x >> 5)) * kMaskRows * 32 + (threadIdx.x & 31);
-    for (;;)
+    unsigned blk = blockIdx.x; // first block static, the following ones from the work counter (fetched one block ahead)
+    while (blk < a.numBlocks)
     {
-        __syncthreads(); // the previous block's shared-memory state is dead
-        if (threadIdx.x == 0) s.nextBlock = atomicAdd(&a.scal->work[kSearchWork], 1u);
-        __syncthreads();
-        const unsigned blk = s.nextBlock;
-        if (blk >= a.numBlocks) break;
+        unsigned nxt = 0;
+        if (threadIdx.x == 0) nxt = gridDim.x + atomicAdd(&a.scal->work[kSearchWork], 1u);
         searchBlock<IterateH>(a, s, blk, maskCol);
+        __syncthreads(); // the block's shared-memory state is dead
+        if (threadIdx.x == 0) s.nextBlock = nxt;
+        __syncthreads();
+        blk = s.nextBlock;
     }
 }
 
@@ -775,7 +788,7 @@ cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, c
     s.tree = a.tree;
     s.x = a.f.x, s.y = a.f.y, s.z = a.f.z, s.h = a.f.h, s.nc = a.f.nc;
     s.ng0 = a.p.ng0, s.ngmax = a.p.ngmax, s.nkbMax = w.nkbMax, s.numBlocks = w.numBlocks;
-    s.maskScratch  = reinterpret_cast<unsigned*>(base + w.maskOff);
+    s.maskScratch  = reinterpret_cast<uint2*>(base + w.maskOff);
     s.list         = reinterpret_cast<uint4*>(base + w.listOff);
     s.cand         = reinterpret_cast<float4*>(base + w.candOff);
     s.candCapacity = unsigned(w.candCapacity > 0xffffffffull ? 0xffffffffull : w.candCapacity);

@@ -30,7 +30,7 @@ constexpr int      kBlockTargets   = 128; // targets per block (T)
 constexpr int      kGroupsPerBlock = kBlockTargets / int(kGroupSize);
 constexpr unsigned kCandPerTarget  = 16;  // candidate-array capacity per assigned particle (typical use: 8-10)
 constexpr unsigned kMaxNgmaxStep   = 384; // list vectors per target: (ngmax + 8) / 8 <= 49
-constexpr unsigned kMaskRows       = 128; // hit-mask rows (32 staged particles each) per warp of the block search
+constexpr unsigned kMaskRows       = 128; // hit-mask entries {mask, word} per target of the block search
 constexpr unsigned kSearchMaxCtas  = 1024; // resident CTAs of the persistent block search (each owns a scratch slice)
 constexpr int      kSearchWork     = 5;   // StepScalars::work slot of the block search (0..4: the loop kernels)
 
@@ -73,7 +73,7 @@ struct WorkspaceLayout
         maskOff      = alignUp(candOff + candCapacity * 16, 256);
         // hit-mask scratch of the block search: one slice per resident CTA, L2-resident (written and read once per block)
         size_t ctas  = numBlocks < kSearchMaxCtas ? numBlocks : kSearchMaxCtas;
-        total        = alignUp(maskOff + ctas * kBlockTargets * kMaskRows * sizeof(unsigned), 256);
+        total        = alignUp(maskOff + ctas * kBlockTargets * kMaskRows * sizeof(uint2), 256);
     }
 };
 
