@@ -159,6 +159,50 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def measure_next_rows(sx, cases, side, dev, peak, reps=5) -> dict:
+    """"report domain::sync and integrate separately". The callers of the hot path (8f rows 1-3) timed on
+    their own Simulation object: device Domain::sync (keys, radix sort, octree), the field reorder, integrate
+    (positions + energy + smoothing length, one fused pass) and the conserved-quantity reduction. Not part of `value`."""
+    import torch
+    s = cases.make_sedov_sim(sx, side, device=dev)
+    s.step()  # sorts the lattice, gives every field a value
+    torch.cuda.synchronize()
+    names = ["domain_sync", "hydro_step", "conserved", "integrate"]
+    acc = {k: 0.0 for k in names}
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        s.sync()
+        ev[1].record()
+        s.compute_forces()
+        ev[2].record()
+        s.compute_conserved()
+        ev[3].record()
+        s.integrate()
+        ev[4].record()
+        torch.cuda.synchronize()
+        for i, k in enumerate(names):
+            acc[k] += ev[i].elapsed_time(ev[i + 1]) / reps
+    n = s.n
+    # integrate: reads x,y,z (24) x_m1.. (12) a (12) temp (8) du (8) du_m1 (4) h (4) nc (4) = 76 B,
+    # writes x,y,z (24) x_m1.. (12) v (12) temp (8) du_m1 (4) h (4) = 64 B per particle
+    integ_bytes = 140
+    # conserved: x,y,z (24) v (12) m (4) temp (8) nc (4)
+    cons_bytes = 52
+    # sync: keys (read 24, write 8+4) + sort (4 passes x 2 x 12 B) + reorder of 15 fields (100 B read + 100 B write + 4)
+    out = {"ms": acc, "n_particles": n, "tree_nodes": s.tree.num_nodes, "tree_leaves": s.tree.num_leaves,
+           "integrate": {"bytes_per_particle": integ_bytes, "GBps": integ_bytes * n / (acc["integrate"] * 1e-3) / 1e9,
+                         "frac": integ_bytes * n / (acc["integrate"] * 1e-3) / 1e9 / peak},
+           "conserved": {"bytes_per_particle": cons_bytes, "GBps": cons_bytes * n / (acc["conserved"] * 1e-3) / 1e9,
+                         "frac": cons_bytes * n / (acc["conserved"] * 1e-3) / 1e9 / peak},
+           "note": "one rank; domain_sync = Hilbert keys + radix sort + octree build + reorder of 15 fields; "
+                   "integrate = computeTimestep + fused positions/energy/h update; the reference's own CUDA build "
+                   "needs 6.1 ms (domain::sync) + 0.5 ms (Timestep + UpdateQuantities) for the same (profiles/)"}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -372,6 +416,13 @@ def our_arm(args):
                         "compulsory + the 16-bit neighbour list and candidate records this design stores in HBM",
                 "per_kernel": {k: per_kernel(k) for k in PHASES}}
 
+    next_rows = None
+    if world == 1 and not args.no_next_rows:
+        try:
+            next_rows = measure_next_rows(sx, cases, side, dev, peak)
+        except Exception as e:  # noqa: BLE001
+            next_rows = {"error": str(e)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -399,7 +450,7 @@ def our_arm(args):
                       "candidates_per_block_mean": float(bs["numCand"].mean()),
                       "candidates_per_block_max": int(bs["numCand"].max()),
                       "candidates_per_particle": bs["candTop"] / n, "fold_blocks": int((bs["flags"] & 1).sum())},
-            "setup_s": setup_s}
+            "next_rows": next_rows, "setup_s": setup_s}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -416,6 +467,7 @@ def main():
     ap.add_argument("--ref-side", type=int, default=128,
                     help="lattice side of the bounded CPU-reference sample (128^3 = 2.1 M particles, ~1.5 s/step on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip timing Domain::sync / integrate / conserved")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

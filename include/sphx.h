@@ -263,6 +263,118 @@ extern "C"
     void sphx_hilbert_keys_host(const double* x, const double* y, const double* z, size_t n, const SphxBox* box,
                                 uint64_t* keys);
 
+    /* --- Domain::sync on the device, one rank --------------------------------------------------- */
+
+    /* Output buffers of sphx_domain_sync, all DEVICE memory owned by the caller. The tree arrays have room for
+     * `maxNodes` nodes (leaves/layout: maxNodes + 1); they are exactly the arrays SphxTreeView points at. */
+    typedef struct SphxSyncArgs
+    {
+        size_t        n;          /* particles of this rank */
+        SphxBox       box;
+        unsigned      bucketSize; /* bucketSizeFocus of cstone::Domain (64 in sphexa.cpp) */
+        const double* x;          /* positions in their current (pre-sync) order */
+        const double* y;
+        const double* z;
+        uint64_t*     keys;  /* out [n]: Hilbert keys, sorted */
+        unsigned*     order; /* out [n]: SFC permutation, sorted particle i is input particle order[i] */
+        int           maxNodes;
+        uint64_t*     prefixes;       /* out, Warren-Salmon keys, nodes sorted by (level, key) */
+        int*          childOffsets;   /* out */
+        int*          internalToLeaf; /* out */
+        int*          levelRange;     /* out, 23 entries */
+        uint64_t*     leaves;         /* out, numLeafNodes + 1 */
+        unsigned*     layout;         /* out, numLeafNodes + 1 */
+        double*       centers;        /* out, 3 per node */
+        double*       sizes;          /* out, 3 per node */
+        void*         scratch;        /* device, sphx_domain_sync_bytes(n, maxNodes) */
+        size_t        scratchBytes;
+        void*         stream;
+    } SphxSyncArgs;
+
+    size_t sphx_domain_sync_bytes(size_t n, int maxNodes);
+
+    /* The single-rank part of cstone::Domain::sync that feeds the hot path (domain/domain.hpp:181-234,416-428), on the
+     * device: Hilbert keys of all particles (sfc/sfc.hpp:141-178, hilbert.hpp:43-93), stable radix sort -> SFC
+     * permutation (the reference: sfc/sfcsorter / reorder_gpu), the converged cornerstone octree of bucketSize
+     * (tree/csarray.hpp:181-430: every leaf holds <= bucketSize particles, every internal node more), its linked form
+     * sorted by (level, key) (tree/octree.hpp:78-197) and the geometric node centres and half sizes
+     * (sfc/box.hpp:318-334). When boxOut != NULL the limits of the non-periodic dimensions are first recomputed as the
+     * coordinate extrema (makeGlobalBox, sfc/box_mpi.hpp:66-109) and the box that was used is returned there; with
+     * boxOut == NULL a->box is used as given. Fields are NOT moved here: apply `order` with sphx_reorder_fields. Returns
+     * the node counts (host); synchronises the stream. SPHX_ERR_WORKSPACE if the tree needs more than maxNodes nodes. */
+    int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodes, int* numLeafNodes);
+
+    /* dst[k][i] = src[k][order[i]] for `count` <= 16 arrays of elemBytes[k] in {1,2,4,8} bytes per particle: the field
+     * reordering of Domain::sync (domain/domain.hpp:224-230, primitives/gather: GpuSfcSorter::extendMap + gatherGpu).
+     * src[k] and dst[k] must not overlap; the caller swaps the buffers afterwards as the reference does. */
+    int sphx_reorder_fields(const unsigned* order, size_t n, int count, const void* const* src, void* const* dst,
+                            const int* elemBytes, void* stream);
+
+    /* --- integrate() and conserved quantities ----------------------------------------------- */
+
+    /* sph::computeTimestep (sph/include/sph/ts_global.hpp:97-113) without gravity: minDt_new = global min of
+     * {minDtCourant, minDtRho, maxDtIncrease * minDt}; in/out: minDt, minDt_m1, ttot. `comm` may be NULL (one rank),
+     * otherwise the MPI_Allreduce(MIN) becomes an NCCL all-reduce. */
+    struct SphxComm;
+    int sphx_compute_timestep(double minDtCourant, double minDtRho, double maxDtIncrease, double* minDt,
+                              double* minDt_m1, double* ttot, struct SphxComm* comm, void* stream);
+
+    typedef struct SphxIntegrateArgs
+    {
+        double*         x; /* in/out */
+        double*         y;
+        double*         z;
+        float*          x_m1; /* in/out: X_n - X_{n-1} */
+        float*          y_m1;
+        float*          z_m1;
+        float*          vx; /* out (read for the fixed-boundary test) */
+        float*          vy;
+        float*          vz;
+        const float*    ax;
+        const float*    ay;
+        const float*    az;
+        double*         temp;  /* in/out, or NULL */
+        double*         u;     /* in/out, used when temp == NULL; may be NULL too */
+        const double*   du;
+        float*          du_m1; /* in/out */
+        float*          h;     /* in/out of the smoothing-length update */
+        const unsigned* nc;
+        size_t          first, last;
+        SphxBox         box;
+        double          dt;    /* d.minDt after computeTimestep */
+        double          dt_m1; /* d.minDt_m1 */
+        double          gamma;
+        float           muiConst;
+        unsigned        ng0;
+        void*           stream;
+    } SphxIntegrateArgs;
+
+    /* sph::computePositions (sph/include/sph/positions.hpp:177-200, positionUpdate :74-86, energyUpdate :57-63,
+     * fixed-boundary skip :97-107, GPU form positions_gpu.cu:119-170) with the CPU path's fp64 arithmetic */
+    int sphx_compute_positions(const SphxIntegrateArgs* a);
+    /* sph::updateSmoothingLength (sph/include/sph/update_h.hpp:44-53, update_h_gpu.cu:40-49): h = updateH(ng0, nc, h) */
+    int sphx_update_smoothing_length(const SphxIntegrateArgs* a);
+    /* both of the above in ONE pass over the particles: what HydroVeProp::integrate does after computeTimestep
+     * (main/src/propagator/ve_hydro.hpp:206-215) */
+    int sphx_integrate(const SphxIntegrateArgs* a);
+
+    /* sphexa::computeConservedQuantities (main/src/observables/conserved_quantities.hpp:49-177, conserved_gpu.cu) */
+    typedef struct SphxConserved
+    {
+        double        ecin, eint, egrav, etot;
+        double        linmom, angmom; /* norms of the summed vectors */
+        double        linmom3[3], angmom3[3];
+        unsigned long totalNeighbors;
+    } SphxConserved;
+    size_t sphx_conserved_scratch_bytes(void);
+    /* temp (or u when temp == NULL) may be NULL => eint = 0; nc may be NULL => totalNeighbors = 0. `scratch`: device,
+     * sphx_conserved_scratch_bytes(). Deterministic (fixed reduction tree). With `comm` the ten sums are all-reduced
+     * (the reference: MPI_Reduce to rank 0). Synchronises the stream. */
+    int sphx_conserved_quantities(const double* x, const double* y, const double* z, const float* vx, const float* vy,
+                                  const float* vz, const float* m, const double* temp, const double* u,
+                                  const unsigned* nc, size_t first, size_t last, double gamma, float muiConst,
+                                  double egrav, void* scratch, struct SphxComm* comm, void* stream, SphxConserved* out);
+
     /* --- SFC domain decomposition over the GPUs of one node (host side) --------------------------------- */
 
     /* cstone::makeSfcAssignment / uniformBins (domain/include/cstone/domain/domaindecomp.hpp:33-110): contiguous

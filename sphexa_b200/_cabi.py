@@ -53,6 +53,29 @@ class SphxHaloPlan(C.Structure):
                 ("sendBufferBytes", C.c_size_t)]
 
 
+class SphxSyncArgs(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("box", SphxBox), ("bucketSize", C.c_uint), ("x", C.c_void_p), ("y", C.c_void_p),
+                ("z", C.c_void_p), ("keys", C.c_void_p), ("order", C.c_void_p), ("maxNodes", C.c_int),
+                ("prefixes", C.c_void_p), ("childOffsets", C.c_void_p), ("internalToLeaf", C.c_void_p),
+                ("levelRange", C.c_void_p), ("leaves", C.c_void_p), ("layout", C.c_void_p), ("centers", C.c_void_p),
+                ("sizes", C.c_void_p), ("scratch", C.c_void_p), ("scratchBytes", C.c_size_t), ("stream", C.c_void_p)]
+
+
+INTEGRATE_FIELDS = "x y z x_m1 y_m1 z_m1 vx vy vz ax ay az temp u du du_m1 h nc".split()
+
+
+class SphxIntegrateArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in INTEGRATE_FIELDS] + [
+        ("first", C.c_size_t), ("last", C.c_size_t), ("box", SphxBox), ("dt", C.c_double), ("dt_m1", C.c_double),
+        ("gamma", C.c_double), ("muiConst", C.c_float), ("ng0", C.c_uint), ("stream", C.c_void_p)]
+
+
+class SphxConserved(C.Structure):
+    _fields_ = [("ecin", C.c_double), ("eint", C.c_double), ("egrav", C.c_double), ("etot", C.c_double),
+                ("linmom", C.c_double), ("angmom", C.c_double), ("linmom3", C.c_double * 3),
+                ("angmom3", C.c_double * 3), ("totalNeighbors", C.c_ulong)]
+
+
 UNIQUE_ID_BYTES = 128
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
@@ -67,7 +90,10 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
-           "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist"]
+           "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
+           "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_reorder_fields", "sphx_compute_timestep",
+           "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
+           "sphx_conserved_quantities"]
 
 
 class SphxError(RuntimeError):
@@ -121,6 +147,18 @@ def load():
     L.sphx_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.sphx_hydro_step_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_domain_sync_bytes.restype = C.c_size_t
+    L.sphx_domain_sync_bytes.argtypes = [C.c_size_t, C.c_int]
+    L.sphx_domain_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_reorder_fields.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_compute_timestep.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    for name in ("sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.sphx_conserved_scratch_bytes.restype = C.c_size_t
+    L.sphx_conserved_quantities.argtypes = [C.c_void_p] * 10 + [C.c_size_t, C.c_size_t, C.c_double, C.c_float,
+                                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                 C.c_void_p]
     _lib = L
     return L
 

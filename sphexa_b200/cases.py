@@ -8,6 +8,7 @@ init/ directory is otherwise out of scope):
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from . import host
 from .sim import HydroData, Params
@@ -123,3 +124,35 @@ def make_turbulence(sx, side: int, device="cuda:0") -> HydroData:
              vy=(0.3 * cs * np.sin(2 * np.pi * z)).astype(np.float32),
              vz=(0.3 * cs * np.sin(2 * np.pi * x)).astype(np.float32))
     return _finish(sx, x, y, z, [-0.5, 0.5] * 3, [1, 1, 1], p, f, device)
+
+
+def make_sedov_sim(sx, side: int, device="cuda:0"):
+    """Sedov case as a sim.Simulation: particles uploaded in GENERATION order (z-major lattice); the first
+    Simulation.sync() sorts them on the device and builds the tree (sedov_init.hpp:98-131 + sphexa.cpp:141)."""
+    from .sim import Simulation
+
+    g = sedov_global(side)
+    return _make_sim(g, device)
+
+
+def make_noh_sim(sx, side: int, device="cuda:0"):
+    return _make_sim(noh_global(side), device)
+
+
+def _make_sim(g: dict, device):
+    from .sim import Simulation
+
+    n = g["x"].size
+    s = Simulation(n, g["box"], g["boundary"], g["params"], device=device)
+    up = {k: (v if isinstance(v, np.ndarray) and v.shape == (n,) else np.full(n, v)) for k, v in g["fields"].items()}
+    s.set_fields(x=g["x"], y=g["y"], z=g["z"], **up)
+    if "vx" in up:  # x_m1 = v * minDt (noh_init.hpp:86-88, turbulence_init.hpp:96-98); zero for Sedov
+        p = g["params"]
+        s.set_fields(x_m1=(up["vx"].astype(np.float64) * p.minDt).astype(np.float32),
+                     y_m1=(up["vy"].astype(np.float64) * p.minDt).astype(np.float32),
+                     z_m1=(up["vz"].astype(np.float64) * p.minDt).astype(np.float32))
+    # the reference initialisers SFC-sort the coordinates first (syncCoords, init/utils.hpp) and number the particles
+    # afterwards (generateParticleIDs, sedov_init.hpp:76): ids are SFC ranks of the initial state
+    s.sync()
+    s.f["id"].copy_(torch.arange(n, dtype=torch.int64, device=s.device))
+    return s

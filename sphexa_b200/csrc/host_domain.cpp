@@ -177,6 +177,25 @@ void computeKeys(const double* x, const double* y, const double* z, size_t n, co
 
 } // namespace
 
+namespace sphx
+{
+//! the Hilbert state machine as flat [state * 8 + octant] arrays for the device (domain_sync.cu); returns #states
+int hilbertTablesFlat(uint8_t* digit, uint8_t* next, uint8_t* octant, int maxStates)
+{
+    const auto& t  = tables();
+    int         ns = int(t.digit.size());
+    if (ns > maxStates) return -1;
+    for (int s = 0; s < ns; ++s)
+        for (int b = 0; b < 8; ++b)
+        {
+            digit[s * 8 + b]  = t.digit[s][b];
+            next[s * 8 + b]   = t.next[s][b];
+            octant[s * 8 + b] = t.octant[s][b];
+        }
+    return ns;
+}
+} // namespace sphx
+
 struct SphxHostTree
 {
     std::vector<unsigned> order;

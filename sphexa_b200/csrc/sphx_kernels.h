@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <string>
 
 #include "sphx.h"
@@ -38,5 +39,8 @@ void        launchEos(const SphxStepArgs& a, cudaStream_t s);
 cudaError_t launchIadDivvCurlv(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchAvSwitches(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchMomentumEnergy(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+
+// Hilbert state machine tables for the device (host_domain.cpp)
+int hilbertTablesFlat(uint8_t* digit, uint8_t* next, uint8_t* octant, int maxStates);
 
 } // namespace sphx

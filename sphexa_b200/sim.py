@@ -79,6 +79,33 @@ class DeviceTree:
         self.centers = up(t["tree_centers"], np.float64)
         self.sizes = up(t["tree_sizes"], np.float64)
 
+    @classmethod
+    def empty(cls, max_nodes: int, device) -> "DeviceTree":
+        """uninitialised buffers for sphx_domain_sync (capacity max_nodes)"""
+        t = cls.__new__(cls)
+        t.num_leaves = t.num_nodes = 0
+        t.max_nodes = int(max_nodes)
+        mk = lambda n, dt: torch.zeros(n, dtype=dt, device=device)  # noqa: E731
+        t.prefixes = mk(max_nodes, torch.int64)
+        t.childOffsets = mk(max_nodes, torch.int32)
+        t.internalToLeaf = mk(max_nodes, torch.int32)
+        t.levelRange = mk(23, torch.int32)
+        t.leaves = mk(max_nodes + 1, torch.int64)
+        t.layout = mk(max_nodes + 1, torch.int32)
+        t.centers = mk(3 * max_nodes, torch.float64)
+        t.sizes = mk(3 * max_nodes, torch.float64)
+        return t
+
+    def to_host(self) -> dict:
+        """the arrays in the reference-harness dump naming (tests), trimmed to the node counts"""
+        nn, nl = self.num_nodes, self.num_leaves
+        cpu = lambda t, k, dt: t[:k].cpu().numpy().view(dt)  # noqa: E731
+        return dict(tree_prefixes=cpu(self.prefixes, nn, np.uint64), tree_childOffsets=cpu(self.childOffsets, nn, np.int32),
+                    tree_internalToLeaf=cpu(self.internalToLeaf, nn, np.int32),
+                    tree_levelRange=cpu(self.levelRange, 23, np.int32), tree_leaves=cpu(self.leaves, nl + 1, np.uint64),
+                    tree_layout=cpu(self.layout, nl + 1, np.uint32), tree_centers=cpu(self.centers, 3 * nn, np.float64),
+                    tree_sizes=cpu(self.sizes, 3 * nn, np.float64))
+
     def view(self) -> _cabi.SphxTreeView:
         v = _cabi.SphxTreeView()
         v.numLeafNodes, v.numNodes = self.num_leaves, self.num_nodes
@@ -208,6 +235,113 @@ class HydroData:
         _cabi.check(self.L.sphx_export_neighbors(C.byref(a), C.c_void_p(out.data_ptr())))
         torch.cuda.synchronize(self.device)
         return out.cpu().numpy().view(np.uint32)
+
+
+class Simulation(HydroData):
+    """One rank of the reference's time-step loop (main/src/sphexa/sphexa.cpp:141-170 with HydroVeProp,
+    main/src/propagator/ve_hydro.hpp:114-215), every stage a libsphx call on device-resident fields:
+    sync (sphx_domain_sync + sphx_reorder_fields) -> computeForces (sphx_hydro_step) -> conserved quantities ->
+    integrate (sphx_compute_timestep + sphx_integrate)."""
+
+    #: fields Domain::sync keeps ordered (ve_hydro.hpp:72-76 conserved fields + coordinates, h, m and the particle id)
+    SYNC_FIELDS = ("x", "y", "z", "h", "m", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "temp", "alpha", "id")
+
+    def __init__(self, n: int, box_lim, boundary, params: Params, device="cuda:0", bucket_size: int = 64):
+        super().__init__(n, 0, n, box_lim, boundary, params, device=device)
+        dev = self.device
+        for name in ("x_m1", "y_m1", "z_m1", "du_m1"):
+            self.f[name] = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.f["id"] = torch.arange(n, dtype=torch.int64, device=dev)
+        self.spare = {k: torch.empty_like(self.f[k]) for k in self.SYNC_FIELDS}
+        self.bucket_size = bucket_size
+        self.keys = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.order = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._alloc_tree(max(4096, n // 4))
+        self.cons_scratch = torch.zeros(self.L.sphx_conserved_scratch_bytes(), dtype=torch.uint8, device=dev)
+        self.conserved = _cabi.SphxConserved()
+        self.iteration = 0
+
+    def _alloc_tree(self, max_nodes: int):
+        self.tree = DeviceTree.empty(max_nodes, self.device)
+        nbytes = self.L.sphx_domain_sync_bytes(self.n, max_nodes)
+        self.sync_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def sync(self):
+        """Domain::sync for one rank: keys, SFC order, octree (sphx_domain_sync), then the field reorder."""
+        while True:
+            t = self.tree
+            a = _cabi.SphxSyncArgs()
+            a.n, a.box, a.bucketSize = self.n, host.make_box(self.box_lim, self.boundary), self.bucket_size
+            a.x, a.y, a.z = (self.f[k].data_ptr() for k in "xyz")
+            a.keys, a.order, a.maxNodes = self.keys.data_ptr(), self.order.data_ptr(), t.max_nodes
+            for k in ("prefixes", "childOffsets", "internalToLeaf", "levelRange", "leaves", "layout", "centers", "sizes"):
+                setattr(a, k, getattr(t, k).data_ptr())
+            a.scratch, a.scratchBytes = self.sync_scratch.data_ptr(), self.sync_scratch.numel()
+            a.stream = self.stream.cuda_stream if self.stream is not None else None
+            nn, nl, box = C.c_int(0), C.c_int(0), _cabi.SphxBox()
+            rc = self.L.sphx_domain_sync(C.byref(a), C.byref(box), C.byref(nn), C.byref(nl))
+            if rc == 4 and t.max_nodes < 8 * self.n + 64:  # SPHX_ERR_WORKSPACE: grow the tree buffers
+                self._alloc_tree(2 * t.max_nodes)
+                continue
+            _cabi.check(rc)
+            t.num_nodes, t.num_leaves = nn.value, nl.value
+            self.box_lim = [float(v) for v in box.lim]  # open dimensions follow the particles (makeGlobalBox)
+            break
+        names = self.SYNC_FIELDS
+        src = (C.c_void_p * len(names))(*[self.f[k].data_ptr() for k in names])
+        dst = (C.c_void_p * len(names))(*[self.spare[k].data_ptr() for k in names])
+        eb = (C.c_int * len(names))(*[self.f[k].element_size() for k in names])
+        _cabi.check(self.L.sphx_reorder_fields(self.order.data_ptr(), self.n, len(names), src, dst, eb, a.stream))
+        for k in names:
+            self.f[k], self.spare[k] = self.spare[k], self.f[k]
+
+    def compute_forces(self):
+        """HydroVeProp::computeForces after sync (ve_hydro.hpp:130-204)"""
+        return self.hydro_step()
+
+    def compute_conserved(self) -> _cabi.SphxConserved:
+        f = self.f
+        _cabi.check(self.L.sphx_conserved_quantities(
+            f["x"].data_ptr(), f["y"].data_ptr(), f["z"].data_ptr(), f["vx"].data_ptr(), f["vy"].data_ptr(),
+            f["vz"].data_ptr(), f["m"].data_ptr(), f["temp"].data_ptr(), None, f["nc"].data_ptr(), self.first, self.last,
+            self.p.gamma, self.p.muiConst, 0.0, self.cons_scratch.data_ptr(), None,
+            self.stream.cuda_stream if self.stream is not None else None, C.byref(self.conserved)))
+        return self.conserved
+
+    def integrate_args(self) -> _cabi.SphxIntegrateArgs:
+        a = _cabi.SphxIntegrateArgs()
+        for k in _cabi.INTEGRATE_FIELDS:
+            setattr(a, k, self.f[k].data_ptr() if k in self.f else None)
+        a.first, a.last, a.box = self.first, self.last, host.make_box(self.box_lim, self.boundary)
+        a.dt, a.dt_m1, a.gamma, a.muiConst, a.ng0 = self.p.minDt, self.p.minDt_m1, self.p.gamma, self.p.muiConst, self.p.ng0
+        a.stream = self.stream.cuda_stream if self.stream is not None else None
+        return a
+
+    def compute_timestep(self):
+        dt, dt1, tt = C.c_double(self.p.minDt), C.c_double(self.p.minDt_m1), C.c_double(self.p.ttot)
+        _cabi.check(self.L.sphx_compute_timestep(self.result.minDtCourant, self.result.minDtRho, self.p.maxDtIncrease,
+                                                 C.byref(dt), C.byref(dt1), C.byref(tt), None, None))
+        self.p.minDt, self.p.minDt_m1, self.p.ttot = dt.value, dt1.value, tt.value
+
+    def integrate(self, fused=True):
+        """HydroVeProp::integrate (ve_hydro.hpp:206-215)"""
+        self.compute_timestep()
+        a = self.integrate_args()
+        if fused:
+            _cabi.check(self.L.sphx_integrate(C.byref(a)))
+        else:
+            _cabi.check(self.L.sphx_compute_positions(C.byref(a)))
+            _cabi.check(self.L.sphx_update_smoothing_length(C.byref(a)))
+
+    def step(self):
+        """one iteration of the main loop; returns the conserved quantities of the state the step started from"""
+        self.sync()
+        self.compute_forces()
+        c = self.compute_conserved()
+        row = (self.iteration, self.p.ttot, self.p.minDt, c.etot, c.ecin, c.eint, c.linmom, c.angmom, c.totalNeighbors)
+        self.integrate()
+        self.iteration += 1
+        return row
 
 
 def from_dump(d: dict, device="cuda:0") -> HydroData:
