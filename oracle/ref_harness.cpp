@@ -10,7 +10,8 @@
  *   (main/src/propagator/ve_hydro.hpp:130-215) including the release/acquire aliasing, with a snapshot of every
  *   output right after the stage that produces it (gradh, divv, curlv are recycled before computeForces returns).
  *
- * Usage: ref_harness <case> <n> <steps> <outdir> [dumpEvery=1] [dumpNeighbors=1] [hscale=1]
+ * Usage: ref_harness <case> <n> <steps> <outdir> [dumpEvery=1] [dumpNeighbors=1] [hscale=1] [avClean=0]
+ *   avClean=1 runs HydroVeProp<true,...>: dV11..dV33 active (ve_hydro.hpp:78-83), computeMomentumEnergy<true>
  *   hscale != 1 perturbs the initial smoothing lengths (h*=hscale if id%3==0, h/=hscale if id%3==1) so that the
  *   coupled h / neighbour-count iteration of sph/find_neighbors.hpp:17-36 is exercised in both directions
  *   case: sedov | noh | turb ; n: cube side; steps: number of hydro steps;
@@ -125,6 +126,7 @@ int main(int argc, char** argv)
     int         dumpEvery = argc > 5 ? std::stoi(argv[5]) : 1;
     bool        dumpNb    = argc > 6 ? std::stoi(argv[6]) != 0 : true;
     double      hscale    = argc > 7 ? std::stod(argv[7]) : 1.0;
+    bool        avClean   = argc > 8 ? std::stoi(argv[8]) != 0 : false;
 
     MPI_Init(&argc, &argv);
     fs::create_directories(outDir);
@@ -138,6 +140,7 @@ int main(int argc, char** argv)
     d.setDependent("keys");
     d.setConserved("temp", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "alpha", "id");
     d.setDependent("ax", "ay", "az", "prho", "c", "du", "c11", "c12", "c13", "c22", "c23", "c33", "xm", "kx", "nc");
+    if (avClean) { d.setDependent("dV11", "dV12", "dV13", "dV22", "dV23", "dV33"); }
 
     cstone::Box<T> box(0, 1);
     if (testCase == "sedov")
@@ -218,11 +221,20 @@ int main(int argc, char** argv)
 
     auto sync = [&]()
     {
-        domain.sync(get<"keys">(d), get<"x">(d), get<"y">(d), get<"z">(d), get<"h">(d),
-                    std::tuple_cat(std::tie(get<"m">(d)),
-                                   get<"temp", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "alpha", "id">(d)),
-                    get<"ax", "ay", "az", "prho", "c", "du", "c11", "c12", "c13", "c22", "c23", "c33", "xm", "kx",
-                        "nc">(d));
+        auto conserved = std::tuple_cat(
+            std::tie(get<"m">(d)), get<"temp", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "alpha", "id">(d));
+        if (avClean)
+        {
+            domain.sync(get<"keys">(d), get<"x">(d), get<"y">(d), get<"z">(d), get<"h">(d), conserved,
+                        get<"ax", "ay", "az", "prho", "c", "du", "c11", "c12", "c13", "c22", "c23", "c33", "xm", "kx",
+                            "nc", "dV11", "dV12", "dV13", "dV22", "dV23", "dV33">(d));
+        }
+        else
+        {
+            domain.sync(get<"keys">(d), get<"x">(d), get<"y">(d), get<"z">(d), get<"h">(d), conserved,
+                        get<"ax", "ay", "az", "prho", "c", "du", "c11", "c12", "c13", "c22", "c23", "c33", "xm", "kx",
+                            "nc">(d));
+        }
         d.treeView = domain.octreeProperties();
     };
 
@@ -347,6 +359,15 @@ int main(int argc, char** argv)
             dump->put("c33", d.c33, first, last);
             dump->put("divv", d.divv, first, last);
             dump->put("curlv", d.curlv, first, last);
+            if (avClean)
+            {
+                dump->put("dV11", d.dV11, first, last);
+                dump->put("dV12", d.dV12, first, last);
+                dump->put("dV13", d.dV13, first, last);
+                dump->put("dV22", d.dV22, first, last);
+                dump->put("dV23", d.dV23, first, last);
+                dump->put("dV33", d.dV33, first, last);
+            }
         }
 
         computeAVswitches(groups.view(), d, box);
@@ -354,7 +375,8 @@ int main(int argc, char** argv)
 
         release(d, "divv", "curlv");
         acquire(d, "ay", "az");
-        computeMomentumEnergy<false>(groups.view(), nullptr, d, box);
+        if (avClean) { computeMomentumEnergy<true>(groups.view(), nullptr, d, box); }
+        else { computeMomentumEnergy<false>(groups.view(), nullptr, d, box); }
         auto t3 = std::chrono::steady_clock::now();
         if (doDump)
         {

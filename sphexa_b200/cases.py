@@ -84,6 +84,23 @@ def noh_global(side: int) -> dict:
     return dict(x=x, y=y, z=z, fields=f, params=p, box=[-0.5, 0.5] * 3, boundary=[0, 0, 0])
 
 
+def turbulence_global(side: int) -> dict:
+    """turbulence box (see make_turbulence) as a host-side description"""
+    p = Params(minDt=1e-4, minDt_m1=1e-4, gamma=1.001, muiConst=0.62, Kcour=0.4)
+    x, y, z = jittered_lattice(0.5, side)
+    fold = lambda a: np.where(a > 0.5, a - 1.0, np.where(a < -0.5, a + 1.0, a))  # noqa: E731  putInBox
+    x, y, z = fold(x), fold(y), fold(z)
+    n = x.size
+    hInit = np.cbrt(3.0 / (4 * np.pi) * p.ng0 * 1.0 / n) * 0.5
+    cv = ideal_gas_cv(p.muiConst, p.gamma)
+    cs = np.sqrt(p.gamma * (p.gamma - 1.0) * 1000.0)
+    f = dict(h=np.float32(hInit), m=np.float32(1.0 / n), temp=np.float64(1000.0) / np.float64(cv),
+             alpha=np.float32(p.alphamin), vx=(0.3 * cs * np.sin(2 * np.pi * y)).astype(np.float32),
+             vy=(0.3 * cs * np.sin(2 * np.pi * z)).astype(np.float32),
+             vz=(0.3 * cs * np.sin(2 * np.pi * x)).astype(np.float32))
+    return dict(x=x, y=y, z=z, fields=f, params=p, box=[-0.5, 0.5] * 3, boundary=[1, 1, 1])
+
+
 def make_sedov(sx, side: int, device="cuda:0") -> HydroData:
     """Sedov blast wave on a side^3 lattice, periodic box (-0.5, 0.5)^3 (sedov_init.hpp:98-131)."""
     p = Params(minDt=1e-6, minDt_m1=1e-6, gamma=5.0 / 3.0, muiConst=10.0)
@@ -137,6 +154,10 @@ def make_sedov_sim(sx, side: int, device="cuda:0"):
 
 def make_noh_sim(sx, side: int, device="cuda:0"):
     return _make_sim(noh_global(side), device)
+
+
+def make_turbulence_sim(sx, side: int, device="cuda:0"):
+    return _make_sim(turbulence_global(side), device)
 
 
 def _make_sim(g: dict, device):

@@ -52,7 +52,7 @@ class Params:
         return Params(K=v[0], Kcour=v[1], Krho=v[2], gamma=v[3], muiConst=v[4], minDt=v[5], minDt_m1=v[6],
                       alphamin=v[7], alphamax=v[8], decay_constant=v[9], Atmin=v[10], Atmax=v[11], ramp=v[12],
                       ttot=v[13], eosChoice=int(v[14]), maxDtIncrease=v[15], ng0=int(d["ng0"][0]),
-                      ngmax=int(d["ngmax"][0]))
+                      ngmax=int(d["ngmax"][0]), avClean=int("dV11" in d))
 
     def to_c(self) -> _cabi.SphxParams:
         p = _cabi.SphxParams()
@@ -128,7 +128,7 @@ class HydroData:
         self.p = params
         self.f: dict[str, torch.Tensor] = {}
         for name in _cabi.FIELD_NAMES:
-            if name in ("u", "rho", "p") or name.startswith("dV"):
+            if name in ("u", "rho", "p") or (name.startswith("dV") and not params.avClean):
                 continue
             dt = torch.float64 if name in F64_FIELDS else (torch.int32 if name in U32_FIELDS else torch.float32)
             self.f[name] = torch.zeros(n_local, dtype=dt, device=self.device)
@@ -229,12 +229,16 @@ class HydroData:
                     candBegin=desc["candBegin"].copy(), candTop=int(scal[28:32].view(np.uint32)[0]),
                     errFlags=int(scal[24:28].view(np.uint32)[0]), candCapacity=int(lay[7]))
 
-    def export_neighbors(self) -> np.ndarray:
+    def export_neighbors_device(self) -> torch.Tensor:
+        """the neighbour list in the reference CPU layout [(i - first) * ngmax + k], as an int32 device tensor"""
         out = torch.zeros((self.last - self.first) * self.p.ngmax, dtype=torch.int32, device=self.device)
         a = self.args()
         _cabi.check(self.L.sphx_export_neighbors(C.byref(a), C.c_void_p(out.data_ptr())))
         torch.cuda.synchronize(self.device)
-        return out.cpu().numpy().view(np.uint32)
+        return out
+
+    def export_neighbors(self) -> np.ndarray:
+        return self.export_neighbors_device().cpu().numpy().view(np.uint32)
 
 
 class Simulation(HydroData):
@@ -352,6 +356,17 @@ def from_dump(d: dict, device="cuda:0") -> HydroData:
                   temp=d["temp"], alpha=d["alpha_in"])
     hd.set_tree(d)
     return hd
+
+
+def simulation_from_dump(d: dict, device="cuda:0") -> Simulation:
+    """Simulation holding the state a reference-harness dump starts its step from (single rank)."""
+    n = int(d["n"][0])
+    s = Simulation(n, d["box"], d["boundary"], Params.from_dump(d), device=device)
+    s.set_fields(x=d["x"], y=d["y"], z=d["z"], h=d["h_in"], m=d["m"], vx=d["vx"], vy=d["vy"], vz=d["vz"],
+                 temp=d["temp"], alpha=d["alpha_in"], x_m1=d["x_m1"], y_m1=d["y_m1"], z_m1=d["z_m1"],
+                 du_m1=d["du_m1"])
+    s.f["id"].copy_(torch.from_numpy(d["id"].view(np.int64)))
+    return s
 
 
 def find_neighbors(x, y, z, h, tree: DeviceTree, box_lim, boundary, ngmax: int, first=0, last=None, device="cuda:0"):

@@ -9,7 +9,11 @@ Outputs (committed):
   noh14_step0.npz      | inputs, tree view, nc, sorted CSR neighbour lists, every loop output, post-integrate state
   turb12_step0.npz     |
   turb12h_step0.npz   /  (hscale=1.6: exercises the h-iteration both ways)
+  turb12av_step0.npz     the same with avClean = true (HydroVeProp<true>: dV11..dV33, computeMomentumEnergy<true>)
   sedov16_energies.npz  etot/ecin/eint series over 30 steps
+  sedov50_energies.npz  the same over 100 steps of BASELINE config 0 (sedov -n 50)
+  noh14_energies.npz, turb12_energies.npz  40 steps continuing noh14_step0 / turb12_step0 (open box that follows the
+                        particles; periodic box with a velocity field)
 """
 import subprocess
 import sys
@@ -69,10 +73,11 @@ def pack_step(d: dict) -> dict:
 
 def make_steps():
     with tempfile.TemporaryDirectory() as tmp:
-        for case, n, steps, keep, hs in [("sedov", 12, 3, (0, 2), 1.0), ("noh", 14, 1, (0,), 1.0),
-                                         ("turb", 12, 1, (0,), 1.0), ("turb", 12, 1, (0,), 1.6)]:
-            tag = f"{case}{n}" + ("" if hs == 1.0 else "h")
-            dumps = run_ref_harness(case, n, steps, Path(tmp) / tag, hscale=hs)
+        for case, n, steps, keep, hs, av in [("sedov", 12, 3, (0, 2), 1.0, False), ("noh", 14, 1, (0,), 1.0, False),
+                                             ("turb", 12, 1, (0,), 1.0, False), ("turb", 12, 1, (0,), 1.6, False),
+                                             ("turb", 12, 1, (0,), 1.0, True)]:
+            tag = f"{case}{n}" + ("" if hs == 1.0 else "h") + ("av" if av else "")
+            dumps = run_ref_harness(case, n, steps, Path(tmp) / tag, hscale=hs, av_clean=av)
             for k in keep:
                 d = pack_step(dumps[k])
                 if not (case == "sedov" and k == 0):
@@ -81,8 +86,12 @@ def make_steps():
         out = Path(tmp) / "sedov16"
         run_ref_harness("sedov", 16, 30, out, dump_every=1000, dump_neighbors=False)
         e = np.loadtxt(out / "energies.txt")
-        np.savez_compressed(GOLDEN / "sedov16_energies.npz", series=e,
-                            columns=np.array("step ttot minDt etot ecin eint linmom angmom totalNeighbors".split()))
+        cols = np.array("step ttot minDt etot ecin eint linmom angmom totalNeighbors".split())
+        np.savez_compressed(GOLDEN / "sedov16_energies.npz", series=e, columns=cols)
+        for case, n, steps, tag in [("sedov", 50, 100, "sedov50"), ("noh", 14, 40, "noh14"), ("turb", 12, 40, "turb12")]:
+            out = Path(tmp) / (tag + "_e")
+            run_ref_harness(case, n, steps, out, dump_every=100000, dump_neighbors=False)
+            np.savez_compressed(GOLDEN / f"{tag}_energies.npz", series=np.loadtxt(out / "energies.txt"), columns=cols)
 
 
 if __name__ == "__main__":

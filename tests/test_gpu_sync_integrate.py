@@ -289,3 +289,22 @@ def test_simulation_sedov50_energy_100_steps(sx):
     # conservation itself, as the reference conserves it
     assert abs(got[-1, 3] / got[0, 3] - 1.0) < 5e-4
     assert abs((got[-1, 3] - got[0, 3]) - (ref[-1, 3] - ref[0, 3])) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["noh14", "turb12"])
+def test_simulation_noh_turbulence_energy_series(sx, tag):
+    """the native loop continued from the reference's step-0 state for 40 steps: Noh (open box that follows the
+    particles through makeGlobalBox in every sync, strong compression) and the turbulence box (periodic, v != 0)"""
+    from sphexa_b200 import sim
+    d = load_golden(f"{tag}_step0.npz")
+    with np.load(GOLDEN / f"{tag}_energies.npz") as z:
+        ref = z["series"]
+    s = sim.simulation_from_dump(d)
+    got = np.array([s.step() for _ in range(ref.shape[0])], dtype=np.float64)
+    np.testing.assert_allclose(got[:, 2], ref[:, 2], rtol=2e-5)             # minDt
+    np.testing.assert_allclose(got[:, 3], ref[:, 3], rtol=1e-6)             # etot
+    np.testing.assert_allclose(got[:, 4], ref[:, 4], rtol=2e-5)             # ecin
+    np.testing.assert_allclose(got[:, 5], ref[:, 5], rtol=2e-5, atol=1e-18)  # eint
+    np.testing.assert_allclose(got[:, 6], ref[:, 6], rtol=1e-4)             # |linear momentum| (non-zero in both cases)
+    assert np.array_equal(got[:3, 8], ref[:3, 8])
+    np.testing.assert_allclose(got[:, 8], ref[:, 8], rtol=2e-3)
