@@ -108,7 +108,7 @@ def make_sedov(sx, side: int, device="cuda:0") -> HydroData:
     return _finish(sx, x, y, z, [-0.5, 0.5] * 3, [1, 1, 1], p, sedov_fields(x, y, z, p), device)
 
 
-def make_noh(sx, side: int, device="cuda:0") -> HydroData:
+def make_noh(sx, side: int, device="cuda:0", bucket_size: int = 64) -> HydroData:
     """Noh implosion: jittered lattice cut to the sphere r <= 0.5, open box (noh_init.hpp:46-103)."""
     p = Params(minDt=1e-4, minDt_m1=1e-4, gamma=5.0 / 3.0, muiConst=10.0)
     x, y, z = jittered_lattice(0.5, side)
@@ -122,7 +122,7 @@ def make_noh(sx, side: int, device="cuda:0") -> HydroData:
     f = dict(h=np.float32(hInit), m=np.float32(1.0 / n), temp=np.float64(1e-20) / np.float64(cv),
              alpha=np.float32(p.alphamin), vx=(-1.0 * (x / radius)).astype(np.float32),
              vy=(-1.0 * (y / radius)).astype(np.float32), vz=(-1.0 * (z / radius)).astype(np.float32))
-    return _finish(sx, x, y, z, [-0.5, 0.5] * 3, [0, 0, 0], p, f, device)
+    return _finish(sx, x, y, z, [-0.5, 0.5] * 3, [0, 0, 0], p, f, device, bucket_size)
 
 
 def make_turbulence(sx, side: int, device="cuda:0") -> HydroData:

@@ -157,6 +157,14 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     double ox = 0, oy = 0, oz = 0;
     bool   foldMode = false;
     int    L = 0;
+    // Fallback for blocks whose targets are NOT compact in space (the SFC leaves the particle distribution and
+    // re-enters it elsewhere, e.g. at the surface of the Noh sphere): their bounding box covers the gap and overlaps
+    // more leaves than the shared-memory tables hold. Such a block repeats the walk in "precise" mode: a node is kept
+    // only if the search sphere of at least one target touches its box. This plays the role of the reference's group
+    // splits (computeGroupSplits, traversal/groups_gpu.cu:106-135), which keep a group's bounding box small.
+    bool    precise = false;
+    float4* tgtSph  = reinterpret_cast<float4*>(s.leafBox + kMaxLeaves); // [T], live during the walk only
+    static_assert((kMaxLeaves + 4 * kBlockTargets) * sizeof(float) <= sizeof(s.leafBox), "target sphere scratch");
 
     for (;;)
     {
@@ -213,6 +221,11 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         const double bcy = 0.5 * (up[1] + lo[1]), bsy = 0.5 * (up[1] - lo[1]);
         const double bcz = 0.5 * (up[2] + lo[2]), bsz = 0.5 * (up[2] - lo[2]);
         ox = bcx, oy = bcy, oz = bcz;
+        if (precise)
+        {
+            const float rr = float(r) * 1.0001f;
+            tgtSph[t]      = make_float4(float(xi - bcx), float(yi - bcy), float(zi - bcz), valid ? rr * rr : -1.0f);
+        }
 
         // ---------------------------------------------------------------------------------------------------------
         // level-synchronous octree walk: nodes overlapping the bounding box (PBC: minimum-image of the centre distance)
@@ -241,6 +254,30 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                                          fabs(dy) <= (a.tree.sizes[3 * node + 1] + bsy) * infl + 1e-300 &&
                                          fabs(dz) <= (a.tree.sizes[3 * node + 2] + bsz) * infl + 1e-300;
                     if (!overlap) continue;
+                    if (precise)
+                    {
+                        // any target sphere within reach of the node box? fp32 relative to the box centre, inflated
+                        const float slop = float(fmax(bsx, fmax(bsy, bsz))) * 8e-6f;
+                        const float ncx = float(dx), ncy = float(dy), ncz = float(dz);
+                        const float hx = __double2float_ru(a.tree.sizes[3 * node]) * 1.00001f + slop;
+                        const float hy = __double2float_ru(a.tree.sizes[3 * node + 1]) * 1.00001f + slop;
+                        const float hz = __double2float_ru(a.tree.sizes[3 * node + 2]) * 1.00001f + slop;
+                        const float plx = float(box.plx), ply = float(box.ply), plz = float(box.plz);
+                        const float ilx = float(box.ilx), ily = float(box.ily), ilz = float(box.ilz);
+                        bool        touch = false;
+                        for (int m = 0; m < T && !touch; ++m)
+                        {
+                            const float4 tg = tgtSph[m];
+                            float        ex = ncx - tg.x, ey = ncy - tg.y, ez = ncz - tg.z;
+                            ex -= plx * rintf(ex * ilx);
+                            ey -= ply * rintf(ey * ily);
+                            ez -= plz * rintf(ez * ilz);
+                            const float qx = fmaxf(fabsf(ex) - hx, 0.0f), qy = fmaxf(fabsf(ey) - hy, 0.0f),
+                                        qz = fmaxf(fabsf(ez) - hz, 0.0f);
+                            touch = qx * qx + qy * qy + qz * qz <= tg.w;
+                        }
+                        if (!touch) continue;
+                    }
                     if (child == 0)
                     {
                         const int li = atomicAdd(&s.nLeaf, 1);
@@ -265,7 +302,13 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             }
         }
         __syncthreads();
-        if (s.err) break;
+        if (s.err)
+        {
+            if (precise) break;
+            precise = true; // uniform: s.err is read after a barrier
+            __syncthreads();
+            continue;
+        }
         L = s.nLeaf;
 
         // ---------------------------------------------------------------------------------------------------------
@@ -375,7 +418,13 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         for (int q = 0; q < kWordsPerThread; ++q)
             s.usedBits[q * T + t] = 0;
         __syncthreads();
-        if (s.err) break;
+        if (s.err)
+        {
+            if (precise) break;
+            precise = true;
+            __syncthreads();
+            continue;
+        }
         const int nTiles = s.nTiles;
 
         // ---------------------------------------------------------------------------------------------------------

@@ -218,6 +218,27 @@ def test_edge_cases(sx):
     assert e.value.code == 4
 
 
+def test_non_compact_blocks_use_the_precise_walk(sx):
+    """Noh sphere, octree of bucket 16: for 36 of the 263 target blocks the SFC leaves the sphere and re-enters it
+    elsewhere, their bounding boxes overlap up to 636 leaves (> the 512 the shared-memory tables hold); the search
+    must fall back to the per-sphere node test (csrc/search.cu, "precise") instead of reporting SPHX_ERR_TRAVERSAL,
+    and the result must not depend on the tree: identical nc, h, neighbour sets as with the bucket-64 tree."""
+    from sphexa_b200 import cases
+    a = cases.make_noh(sx, 40)
+    b = cases.make_noh(sx, 40, bucket_size=16)
+    assert b.tree.num_leaves > 2 * a.tree.num_leaves
+    a.hydro_step()
+    b.hydro_step()
+    np.testing.assert_array_equal(a.get("nc"), b.get("nc"))
+    np.testing.assert_array_equal(a.get("h"), b.get("h"))
+    ngmax = a.p.ngmax
+    na = csr_sorted_neighbors(a.export_neighbors(), a.get("nc"), ngmax)
+    nb = csr_sorted_neighbors(b.export_neighbors(), b.get("nc"), ngmax)
+    np.testing.assert_array_equal(na[0], nb[0])
+    np.testing.assert_array_equal(na[1], nb[1])
+    assert_fields_close({k: b.get(k) for k in F32_FIELDS}, {k: a.get(k) for k in F32_FIELDS})
+
+
 def test_properties_at_scale(sx):
     """Sedov 100^3 lattice (1M particles), no oracle needed: every particle of the periodic lattice has exactly 92
     neighbours + self, neighbour relation is symmetric for equal h, the lattice at rest has zero
