@@ -289,7 +289,11 @@ extern "C"
         void*         scratch;        /* device, sphx_domain_sync_bytes(n, maxNodes) */
         size_t        scratchBytes;
         void*         stream;
+        int           flags; /* SPHX_SYNC_* */
     } SphxSyncArgs;
+
+#define SPHX_SYNC_PRESORTED 1 /* x, y, z are in SFC order already: keys are computed, nothing is sorted, order may be NULL */
+#define SPHX_SYNC_NO_TREE 2   /* keys and SFC order only; the tree buffers may be NULL */
 
     size_t sphx_domain_sync_bytes(size_t n, int maxNodes);
 
@@ -303,6 +307,11 @@ extern "C"
      * boxOut == NULL a->box is used as given. Fields are NOT moved here: apply `order` with sphx_reorder_fields. Returns
      * the node counts (host); synchronises the stream. SPHX_ERR_WORKSPACE if the tree needs more than maxNodes nodes. */
     int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodes, int* numLeafNodes);
+
+    /* counts[c] = number of keys in Hilbert cell c of `level` (8^level cells, cell = key >> 3 (21 - level)) for SFC-sorted
+     * keys; the local histogram behind the global assignment (the reference counts the leaves of its global octree,
+     * domain/include/cstone/tree/csarray.hpp:181-260 computeNodeCounts). level <= 10. */
+    int sphx_cell_histogram(const uint64_t* sortedKeys, size_t n, int level, unsigned* counts, void* stream);
 
     /* dst[k][i] = src[k][order[i]] for `count` <= 16 arrays of elemBytes[k] in {1,2,4,8} bytes per particle: the field
      * reordering of Domain::sync (domain/domain.hpp:224-230, primitives/gather: GpuSfcSorter::extendMap + gatherGpu).
@@ -390,6 +399,27 @@ extern "C"
     int sphx_find_halos_host(const double* x_host, const double* y_host, const double* z_host, const float* h_host,
                              size_t n, const SphxBox* box, unsigned bucketSize, size_t ownedBegin, size_t ownedEnd,
                              unsigned char* flags);
+
+    /* --- dynamic decomposition: the host half of the multi-rank Domain::sync ------------------- */
+
+    /* From the GLOBAL particle count per Hilbert cell of `level` (sphx_cell_histogram + all-reduce), identically on
+     * every rank: balanced contiguous cell ranges (makeSfcAssignment / uniformBins, domaindecomp.hpp:33-110), the halo
+     * cells of `rank` = non-empty foreign cells adjacent (26-neighbourhood, periodic wrap per periodic[3]) to its own
+     * non-empty cells (Halos::discover, halos/halos.hpp:131-192: whole-cell halos; complete if the cell edge is
+     * >= 2 max h), the local layout [halos | assigned | halos] (layout.hpp:150-163) and the SphxHaloPlan arrays: peers,
+     * send lists as local particle indices (valid once the assigned particles sit SFC-sorted at [nHaloLeft,
+     * nHaloLeft + nAssigned)), one contiguous receive range per peer. NULL on bad arguments. */
+    typedef struct SphxCellPlan SphxCellPlan;
+    SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts_host, int level, const int* periodic, int rank,
+                                            int nranks);
+    void          sphx_cell_plan_free(SphxCellPlan*);
+    /* sizes: [0] numPeers [1] send indices [2] halo cells [3] nAssigned [4] nHaloLeft [5] nHaloRight [6] nGlobal
+     * [7] nranks */
+    void sphx_cell_plan_sizes(const SphxCellPlan*, size_t sizes[8]);
+    /* copy out (any pointer may be NULL): cellSplits[nranks + 1], peers[numPeers], sendOffsets[numPeers + 1],
+     * sendIdx[...], recvBegin[numPeers], recvCount[numPeers], recvCells[...] (sorted halo cell ids) */
+    void sphx_cell_plan_get(const SphxCellPlan*, uint64_t* cellSplits, int* peers, unsigned* sendOffsets,
+                            unsigned* sendIdx, unsigned* recvBegin, unsigned* recvCount, unsigned* recvCells);
 
     /* --- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ------------------------------------------------- */
 

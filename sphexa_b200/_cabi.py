@@ -58,7 +58,8 @@ class SphxSyncArgs(C.Structure):
                 ("z", C.c_void_p), ("keys", C.c_void_p), ("order", C.c_void_p), ("maxNodes", C.c_int),
                 ("prefixes", C.c_void_p), ("childOffsets", C.c_void_p), ("internalToLeaf", C.c_void_p),
                 ("levelRange", C.c_void_p), ("leaves", C.c_void_p), ("layout", C.c_void_p), ("centers", C.c_void_p),
-                ("sizes", C.c_void_p), ("scratch", C.c_void_p), ("scratchBytes", C.c_size_t), ("stream", C.c_void_p)]
+                ("sizes", C.c_void_p), ("scratch", C.c_void_p), ("scratchBytes", C.c_size_t), ("stream", C.c_void_p),
+                ("flags", C.c_int)]
 
 
 INTEGRATE_FIELDS = "x y z x_m1 y_m1 z_m1 vx vy vz ax ay az temp u du du_m1 h nc".split()
@@ -91,7 +92,8 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
            "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
-           "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_reorder_fields", "sphx_compute_timestep",
+           "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get",
+           "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
            "sphx_conserved_quantities"]
 
@@ -150,6 +152,12 @@ def load():
     L.sphx_domain_sync_bytes.restype = C.c_size_t
     L.sphx_domain_sync_bytes.argtypes = [C.c_size_t, C.c_int]
     L.sphx_domain_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_cell_plan_build_host.restype = C.c_void_p
+    L.sphx_cell_plan_build_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.sphx_cell_plan_free.argtypes = [C.c_void_p]
+    L.sphx_cell_plan_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.sphx_cell_plan_get.argtypes = [C.c_void_p] * 8
+    L.sphx_cell_histogram.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     L.sphx_reorder_fields.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_compute_timestep.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]

@@ -254,6 +254,17 @@ __global__ void nodeGeometryKernel(NodeArrays nd, int numNodes, const int* __res
     sizes[3 * i + 2]   = __dmul_rn(double(izmax - int(iz)), hz);
 }
 
+//! particles per Hilbert cell of the given level from the sorted keys: two binary searches per cell
+__global__ void cellHistogramKernel(const uint64_t* __restrict__ keys, unsigned n, int shift, unsigned numCells,
+                                    unsigned* __restrict__ counts)
+{
+    unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= numCells) return;
+    unsigned b = lowerBound(keys, 0, n, uint64_t(c) << shift);
+    unsigned e = (c + 1 == numCells) ? n : lowerBound(keys, b, n, uint64_t(c + 1) << shift);
+    counts[c]  = e - b;
+}
+
 struct GatherArgs
 {
     const void* src[16];
@@ -375,11 +386,15 @@ int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodesOut, i
 {
     using namespace sphx;
     if (int st = sphx_device_check()) return st;
-    if (!a || !a->x || !a->y || !a->z || !a->keys || !a->order || !a->childOffsets || !a->internalToLeaf ||
-        !a->levelRange || !a->leaves || !a->layout || !a->centers || !a->sizes || !a->prefixes || !a->scratch)
+    const bool presorted = a && (a->flags & SPHX_SYNC_PRESORTED);
+    const bool noTree    = a && (a->flags & SPHX_SYNC_NO_TREE);
+    if (!a || !a->x || !a->y || !a->z || !a->keys || (!presorted && !a->order) || !a->scratch)
         return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: null argument");
+    if (!noTree && (!a->childOffsets || !a->internalToLeaf || !a->levelRange || !a->leaves || !a->layout ||
+                    !a->centers || !a->sizes || !a->prefixes))
+        return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: null tree buffer");
     if (a->n == 0 || a->n >= (size_t(1) << 31)) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: bad particle count");
-    if (a->maxNodes < 9) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: maxNodes too small");
+    if (!noTree && a->maxNodes < 9) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: maxNodes too small");
     SyncScratch s(a->n, a->maxNodes);
     if (a->scratchBytes < s.total)
         return syncFail(SPHX_ERR_WORKSPACE, "sphx_domain_sync: scratch too small, need " + std::to_string(s.total));
@@ -413,10 +428,27 @@ int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodesOut, i
     kb.lx = box.lim[1] - box.lim[0], kb.ly = box.lim[3] - box.lim[2], kb.lz = box.lim[5] - box.lim[4];
     kb.mx = kMaxCoord * (1.0 / kb.lx), kb.my = kMaxCoord * (1.0 / kb.ly), kb.mz = kMaxCoord * (1.0 / kb.lz);
 
-    hilbertKeysKernel<<<(n + 255) / 256, 256, 0, stream>>>(a->x, a->y, a->z, n, kb, keysIn, iotaIn);
     size_t tempBytes = s.cubTempBytes;
-    SYNC_CUDA(cub::DeviceRadixSort::SortPairs(at(s.cubTemp), tempBytes, keysIn, a->keys, iotaIn, a->order, int(n), 0,
-                                              3 * kMaxLevel, stream));
+    if (presorted)
+    {
+        // particles are in SFC order already (e.g. [halos | assigned | halos] of a rank): keys only
+        hilbertKeysKernel<<<(n + 255) / 256, 256, 0, stream>>>(a->x, a->y, a->z, n, kb, a->keys,
+                                                              a->order ? a->order : iotaIn);
+    }
+    else
+    {
+        hilbertKeysKernel<<<(n + 255) / 256, 256, 0, stream>>>(a->x, a->y, a->z, n, kb, keysIn, iotaIn);
+        SYNC_CUDA(cub::DeviceRadixSort::SortPairs(at(s.cubTemp), tempBytes, keysIn, a->keys, iotaIn, a->order, int(n),
+                                                  0, 3 * kMaxLevel, stream));
+    }
+    if (noTree)
+    {
+        SYNC_CUDA(cudaGetLastError());
+        SYNC_CUDA(cudaStreamSynchronize(stream));
+        if (numNodesOut) *numNodesOut = 0;
+        if (numLeafNodesOut) *numLeafNodesOut = 0;
+        return SPHX_OK;
+    }
 
     // ---- top-down tree ----
     NodeArrays nd{static_cast<uint64_t*>(at(s.nodeStart)), static_cast<unsigned*>(at(s.nodePBegin)),
@@ -483,6 +515,19 @@ int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodesOut, i
     SYNC_CUDA(cudaStreamSynchronize(stream));
     if (numNodesOut) *numNodesOut = numNodes;
     if (numLeafNodesOut) *numLeafNodesOut = numLeaves;
+    return SPHX_OK;
+}
+
+int sphx_cell_histogram(const uint64_t* sortedKeys, size_t n, int level, unsigned* counts, void* stream)
+{
+    using namespace sphx;
+    if (int st = sphx_device_check()) return st;
+    if (!counts || level < 0 || level > 10 || n >= (size_t(1) << 32) || (n && !sortedKeys))
+        return syncFail(SPHX_ERR_INVALID, "sphx_cell_histogram: bad argument");
+    unsigned numCells = 1u << (3 * level);
+    cellHistogramKernel<<<(numCells + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        sortedKeys, unsigned(n), 3 * (kMaxLevel - level), numCells, counts);
+    SYNC_CUDA(cudaGetLastError());
     return SPHX_OK;
 }
 

@@ -481,6 +481,173 @@ int sphx_find_halos_host(const double* x, const double* y, const double* z, cons
     return SPHX_OK;
 }
 
+/* ------------------------------------ cell-based decomposition plan (dynamic, per sync) ------------------------------------ */
+
+/*! The host half of the multi-rank Domain::sync. Ranks agree on a GLOBAL histogram of particles
+ *  per Hilbert cell of one level (device histogram + NCCL all-reduce); from it every rank derives, without further
+ *  communication and identically:
+ *   - the assignment: contiguous cell ranges balanced by particle count (makeSfcAssignment / uniformBins,
+ *     domaindecomp.hpp:33-110, with the cells in the role of the global-tree leaves),
+ *   - its halo cells: every non-empty foreign cell adjacent (26-neighbourhood, periodic wrap) to one of its own
+ *     non-empty cells. The caller picks the level such that a cell edge is >= 2 max(h): then every neighbour of an
+ *     assigned particle lies in an owned or halo cell (Halos::discover, halos/halos.hpp:131-192, whole-cell halos),
+ *   - what it sends: its own cells that are halo cells of a peer (adjacency is symmetric, so no request messages),
+ *   - the local layout [halos | assigned | halos] in SFC order (layout.hpp:150-163) with one contiguous receive range
+ *     per peer, and the send lists as local particle indices. */
+struct SphxCellPlan
+{
+    int                   level, rank, nranks;
+    std::vector<uint64_t> cellSplits; // nranks + 1
+    std::vector<int>      peers;
+    std::vector<unsigned> sendOffsets, sendIdx, recvBegin, recvCount;
+    std::vector<unsigned> recvCells; // sorted
+    size_t                nAssigned{0}, nHaloLeft{0}, nHaloRight{0}, nGlobal{0};
+};
+
+SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level, const int* periodic, int rank,
+                                        int nranks)
+{
+    if (!globalCounts || level < 0 || level > 10 || !periodic || rank < 0 || rank >= nranks) return nullptr;
+    auto*          p      = new SphxCellPlan;
+    const uint64_t ncell  = uint64_t(1) << (3 * level);
+    const int      side   = 1 << level;
+    const int      cshift = kMaxLevel - level;
+    p->level = level, p->rank = rank, p->nranks = nranks;
+
+    std::vector<uint64_t> prefix(ncell + 1);
+    prefix[0] = 0;
+    for (uint64_t c = 0; c < ncell; ++c)
+        prefix[c + 1] = prefix[c] + globalCounts[c];
+    const uint64_t N = prefix[ncell];
+    p->nGlobal       = N;
+
+    // uniformBins: rank r starts at the first cell boundary at or after r N / R particles
+    p->cellSplits.assign(nranks + 1, 0);
+    p->cellSplits[nranks] = ncell;
+    for (int r = 1; r < nranks; ++r)
+    {
+        uint64_t target = uint64_t((__uint128_t(N) * r) / nranks);
+        uint64_t c      = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+        p->cellSplits[r] = std::max(std::min(c, ncell), p->cellSplits[r - 1]);
+    }
+    const uint64_t cb = p->cellSplits[rank], ce = p->cellSplits[rank + 1];
+    p->nAssigned = prefix[ce] - prefix[cb];
+
+    auto ownerOf = [&](uint64_t c)
+    { return int(std::upper_bound(p->cellSplits.begin() + 1, p->cellSplits.end() - 1, c) - (p->cellSplits.begin() + 1)); };
+
+    // adjacency sweep over my non-empty cells
+    std::vector<std::vector<unsigned>> sendCells(nranks);
+    std::vector<unsigned>              recvCells;
+    tables();
+#pragma omp parallel
+    {
+        std::vector<std::vector<unsigned>> mySend(nranks);
+        std::vector<unsigned>              myRecv;
+#pragma omp for schedule(static)
+        for (int64_t c = int64_t(cb); c < int64_t(ce); ++c)
+        {
+            if (globalCounts[c] == 0) continue;
+            unsigned ix, iy, iz;
+            hilbertDecode(uint64_t(c) << (3 * cshift), ix, iy, iz);
+            int cx = int(ix >> cshift), cy = int(iy >> cshift), cz = int(iz >> cshift);
+            int lastOwner = -1; // a cell is listed once per peer: neighbours of one cell often share the owner
+            int sentTo[26], nSent = 0;
+            (void)lastOwner;
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx)
+                    {
+                        if (!dx && !dy && !dz) continue;
+                        int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                        if (nx < 0 || nx >= side) { if (!periodic[0]) continue; nx = (nx + side) % side; }
+                        if (ny < 0 || ny >= side) { if (!periodic[1]) continue; ny = (ny + side) % side; }
+                        if (nz < 0 || nz >= side) { if (!periodic[2]) continue; nz = (nz + side) % side; }
+                        uint64_t c2 = hilbertEncode(unsigned(nx) << cshift, unsigned(ny) << cshift,
+                                                    unsigned(nz) << cshift) >> (3 * cshift);
+                        if (c2 >= cb && c2 < ce) continue;
+                        if (globalCounts[c2] == 0) continue;
+                        myRecv.push_back(unsigned(c2));
+                        int  o    = ownerOf(c2);
+                        bool seen = false;
+                        for (int k = 0; k < nSent; ++k)
+                            seen |= sentTo[k] == o;
+                        if (!seen)
+                        {
+                            sentTo[nSent++] = o;
+                            mySend[o].push_back(unsigned(c));
+                        }
+                    }
+        }
+#pragma omp critical
+        {
+            recvCells.insert(recvCells.end(), myRecv.begin(), myRecv.end());
+            for (int r = 0; r < nranks; ++r)
+                sendCells[r].insert(sendCells[r].end(), mySend[r].begin(), mySend[r].end());
+        }
+    }
+    std::sort(recvCells.begin(), recvCells.end());
+    recvCells.erase(std::unique(recvCells.begin(), recvCells.end()), recvCells.end());
+    for (auto& v : sendCells)
+        std::sort(v.begin(), v.end()); // each of my cells appears at most once per peer
+
+    for (unsigned c : recvCells)
+        (c < cb ? p->nHaloLeft : p->nHaloRight) += globalCounts[c];
+
+    // peers in rank order; receive ranges: recvCells are sorted, a peer's cells are consecutive in that order
+    p->sendOffsets.push_back(0);
+    size_t ri = 0, pos = 0;
+    for (int r = 0; r < nranks; ++r)
+    {
+        if (r == rank)
+        {
+            pos = p->nHaloLeft + p->nAssigned; // right halos follow the assigned range
+            continue;
+        }
+        size_t   begin = pos, cnt = 0;
+        uint64_t rb = p->cellSplits[r], re = p->cellSplits[r + 1];
+        while (ri < recvCells.size() && recvCells[ri] >= rb && recvCells[ri] < re)
+        {
+            cnt += globalCounts[recvCells[ri]];
+            ++ri;
+        }
+        pos += cnt;
+        if (cnt == 0 && sendCells[r].empty()) continue;
+        p->peers.push_back(r);
+        p->recvBegin.push_back(unsigned(begin));
+        p->recvCount.push_back(unsigned(cnt));
+        for (unsigned c : sendCells[r])
+        {
+            unsigned first = unsigned(p->nHaloLeft + (prefix[c] - prefix[cb]));
+            for (unsigned k = 0; k < globalCounts[c]; ++k)
+                p->sendIdx.push_back(first + k);
+        }
+        p->sendOffsets.push_back(unsigned(p->sendIdx.size()));
+    }
+    p->recvCells.swap(recvCells);
+    return p;
+}
+
+void sphx_cell_plan_free(SphxCellPlan* p) { delete p; }
+
+void sphx_cell_plan_sizes(const SphxCellPlan* p, size_t sizes[8])
+{
+    sizes[0] = p->peers.size(), sizes[1] = p->sendIdx.size(), sizes[2] = p->recvCells.size();
+    sizes[3] = p->nAssigned, sizes[4] = p->nHaloLeft, sizes[5] = p->nHaloRight, sizes[6] = p->nGlobal;
+    sizes[7] = size_t(p->nranks);
+}
+
+void sphx_cell_plan_get(const SphxCellPlan* p, uint64_t* cellSplits, int* peers, unsigned* sendOffsets,
+                        unsigned* sendIdx, unsigned* recvBegin, unsigned* recvCount, unsigned* recvCells)
+{
+    auto cp = [](auto* dst, const auto& v)
+    {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    cp(cellSplits, p->cellSplits), cp(peers, p->peers), cp(sendOffsets, p->sendOffsets), cp(sendIdx, p->sendIdx);
+    cp(recvBegin, p->recvBegin), cp(recvCount, p->recvCount), cp(recvCells, p->recvCells);
+}
+
 float sphx_update_h_host(unsigned ng0, unsigned nc, float h) { return sphx::updateHExact(ng0, nc, h); }
 float sphx_powf_host(float x, float y) { return sphx::glibcPowf(x, y); }
 

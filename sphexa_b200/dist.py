@@ -206,3 +206,60 @@ class DistributedHydro:
         if self.comm:
             self.L.sphx_comm_free(self.comm)
             self.comm = C.c_void_p()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dynamic decomposition (multi-rank Domain::sync): cell plan from the global histogram
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class CellPlan:
+    """what sphx_cell_plan_build_host derives for one rank from the global per-cell particle counts"""
+    level: int
+    cell_splits: np.ndarray   # uint64, nranks + 1
+    peers: np.ndarray         # int32
+    send_offsets: np.ndarray  # uint32, numPeers + 1
+    send_idx: np.ndarray      # uint32 local indices (valid in the layout [halos | assigned | halos])
+    recv_begin: np.ndarray    # uint32
+    recv_count: np.ndarray    # uint32
+    recv_cells: np.ndarray    # uint32, sorted halo cells
+    n_assigned: int
+    n_halo_left: int
+    n_halo_right: int
+    n_global: int
+
+    @property
+    def n_local(self):
+        return self.n_halo_left + self.n_assigned + self.n_halo_right
+
+
+def cell_plan(global_counts: np.ndarray, level: int, boundary, rank: int, nranks: int) -> CellPlan:
+    L = _cabi.load()
+    g = np.ascontiguousarray(global_counts, np.uint32)
+    assert g.size == 8 ** level
+    per = np.array([int(b == 1) for b in boundary], np.int32)
+    h = L.sphx_cell_plan_build_host(_p(g), level, _p(per), rank, nranks)
+    if not h:
+        raise ValueError("sphx_cell_plan_build_host: bad arguments")
+    try:
+        sz = np.zeros(8, np.uint64)
+        L.sphx_cell_plan_sizes(h, _p(sz))
+        npeer, nsend, ncells = int(sz[0]), int(sz[1]), int(sz[2])
+        out = CellPlan(level, np.zeros(nranks + 1, np.uint64), np.zeros(npeer, np.int32),
+                       np.zeros(npeer + 1, np.uint32), np.zeros(nsend, np.uint32), np.zeros(npeer, np.uint32),
+                       np.zeros(npeer, np.uint32), np.zeros(ncells, np.uint32), int(sz[3]), int(sz[4]), int(sz[5]),
+                       int(sz[6]))
+        L.sphx_cell_plan_get(h, _p(out.cell_splits), _p(out.peers), _p(out.send_offsets), _p(out.send_idx),
+                             _p(out.recv_begin), _p(out.recv_count), _p(out.recv_cells))
+    finally:
+        L.sphx_cell_plan_free(h)
+    return out
+
+
+def cell_level(box_lim, h_max: float, max_level: int = 7) -> int:
+    """finest level whose cell edge is >= 2 h_max in every dimension (so the 26-neighbourhood covers every search
+    sphere), capped at max_level (8^7 = 2 M cells: the histogram all-reduce and the host sweep stay cheap)"""
+    ext = min(box_lim[1] - box_lim[0], box_lim[3] - box_lim[2], box_lim[5] - box_lim[4])
+    lvl = 0
+    while lvl < max_level and ext / (1 << (lvl + 1)) >= 2.0 * h_max * 1.0001:
+        lvl += 1
+    return lvl
