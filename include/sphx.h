@@ -460,6 +460,19 @@ extern "C"
      * (sph/include/sph/ts_global.hpp:97-113) and of the neighbour statistics. Synchronises the stream. */
     int sphx_allreduce_f64(SphxComm* comm, double* values_host, int n, int op, void* stream);
 
+    /* in-place all-reduce of a DEVICE array (dtype: 0 u32, 1 u64, 2 f32, 3 f64; op: 0 min, 1 max, 2 sum), enqueued on
+     * the stream: the global cell histogram of the dynamic decomposition (the reference: MPI_Allreduce of the global
+     * tree's node counts, domain/include/cstone/tree/update_mpi.hpp) */
+    int sphx_allreduce_device(SphxComm* comm, void* data_dev, size_t n, int dtype, int op, void* stream);
+
+    /* Particle migration of Domain::sync (domain/include/cstone/domain/exchange_keys / domaindecomp_mpi.hpp
+     * exchangeParticles): every rank holds its particles SFC-sorted, so what goes to rank r is ONE slice
+     * [sendOffsets[r], sendOffsets[r+1]) of every field; it lands at [recvOffsets[r], recvOffsets[r+1]) of dst on rank r's
+     * side (offsets in particles, host arrays of nranks + 1 entries; the own slice is copied device to device). One
+     * grouped ncclSend/ncclRecv round per array, everything enqueued on the stream. */
+    int sphx_exchange_slices(SphxComm* comm, const size_t* sendOffsets, const size_t* recvOffsets, int count,
+                             const void* const* src, void* const* dst, const int* elemBytes, void* stream);
+
     /* sphx_hydro_step with the four halo exchanges of HydroVeProp::computeForces (ve_hydro.hpp:154,165,174,185) done
      * by sphx_halo_exchange and the result scalars reduced over all ranks (min dt, sum of neighbours, max nc). */
     int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* comm, const SphxHaloPlan* plan, SphxStepResult* r);

@@ -274,6 +274,53 @@ int sphx_allreduce_f64(SphxComm* c, double* values_host, int n, int op, void* st
     return SPHX_OK;
 }
 
+int sphx_allreduce_device(SphxComm* c, void* data_dev, size_t n, int dtype, int op, void* stream)
+{
+    if (!c || !data_dev || op < 0 || op > 2 || dtype < 0 || dtype > 3) return SPHX_ERR_INVALID;
+    const ncclRedOp_t    ops[3]   = {ncclMin, ncclMax, ncclSum};
+    const ncclDataType_t types[4] = {ncclUint32, ncclUint64, ncclFloat32, ncclFloat64};
+    if (n == 0) return SPHX_OK;
+    SPHX_NCCL(c->api->AllReduce(data_dev, data_dev, n, types[dtype], ops[op], c->comm,
+                                static_cast<cudaStream_t>(stream)));
+    return SPHX_OK;
+}
+
+int sphx_exchange_slices(SphxComm* c, const size_t* sendOffsets, const size_t* recvOffsets, int count,
+                         const void* const* src, void* const* dst, const int* elemBytes, void* stream)
+{
+    if (!c || !sendOffsets || !recvOffsets || count < 0 || (count && (!src || !dst || !elemBytes)))
+        return SPHX_ERR_INVALID;
+    auto s = static_cast<cudaStream_t>(stream);
+    const int me = c->rank;
+    for (int k = 0; k < count; ++k)
+    {
+        const size_t eb = size_t(elemBytes[k]);
+        if (!src[k] || !dst[k] || eb == 0) return SPHX_ERR_INVALID;
+        const char* sp = static_cast<const char*>(src[k]);
+        char*       dp = static_cast<char*>(dst[k]);
+        // the slice that stays
+        size_t own = sendOffsets[me + 1] - sendOffsets[me];
+        if (own != recvOffsets[me + 1] - recvOffsets[me])
+        {
+            g_distError = "sphx_exchange_slices: own slice differs between send and receive layout";
+            return SPHX_ERR_INVALID;
+        }
+        if (own && cudaMemcpyAsync(dp + recvOffsets[me] * eb, sp + sendOffsets[me] * eb, own * eb,
+                                   cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return SPHX_ERR_CUDA;
+        SPHX_NCCL(c->api->GroupStart());
+        for (int r = 0; r < c->nranks; ++r)
+        {
+            if (r == me) continue;
+            size_t ns = sendOffsets[r + 1] - sendOffsets[r], nr = recvOffsets[r + 1] - recvOffsets[r];
+            if (ns) SPHX_NCCL(c->api->Send(sp + sendOffsets[r] * eb, ns * eb, ncclChar, r, c->comm, s));
+            if (nr) SPHX_NCCL(c->api->Recv(dp + recvOffsets[r] * eb, nr * eb, ncclChar, r, c->comm, s));
+        }
+        SPHX_NCCL(c->api->GroupEnd());
+    }
+    return SPHX_OK;
+}
+
 namespace
 {
 struct DistCtx

@@ -263,3 +263,283 @@ def cell_level(box_lim, h_max: float, max_level: int = 7) -> int:
     while lvl < max_level and ext / (1 << (lvl + 1)) >= 2.0 * h_max * 1.0001:
         lvl += 1
     return lvl
+
+
+def init_comm(L, rank: int, nranks: int, device, pg=None):
+    """NCCL communicator of libsphx: rank 0 creates the unique id, the host process group distributes it"""
+    import torch
+    import torch.distributed as dist
+
+    uid = np.zeros(_cabi.UNIQUE_ID_BYTES, np.uint8)
+    if rank == 0:
+        _cabi.check(L.sphx_comm_unique_id(_p(uid)))
+    if nranks > 1:
+        box_ = [uid.tobytes()]
+        dist.broadcast_object_list(box_, src=0, group=pg)
+        uid = np.frombuffer(box_[0], np.uint8).copy()
+    comm = C.c_void_p()
+    torch.cuda.set_device(torch.device(device))
+    _cabi.check(L.sphx_comm_init(C.byref(comm), rank, nranks, _p(uid)))
+    return comm
+
+
+class DistributedSimulation:
+    """One rank of the multi-GPU time-step loop: the reference's main loop (sphexa.cpp:141-170) with a dynamic SFC
+    domain decomposition redone in every sync().
+
+    sync() = multi-rank Domain::sync (domain/domain.hpp:181-234) re-designed around ONE global object, the particle
+    count per Hilbert cell of a level whose cell edge is >= 2 max(h):
+      keys + local radix sort (device) -> cell histogram (device) -> ncclAllReduce -> host plan (assignment, halo
+      cells, send lists, layout: sphx_cell_plan_build_host, no request messages) -> particle migration as one slice
+      per peer and field (sphx_exchange_slices) -> merge sort of the arrivals -> halo exchange of x, y, z, h, m ->
+      octree over the local particles (sphx_domain_sync, presorted).
+    The reference negotiates the same things through a focus octree with peer-to-peer messages.
+    `pg`: torch.distributed group for host-side plumbing only (unique id, the R x R matrix of migration counts)."""
+
+    SYNC_FIELDS = ("x", "y", "z", "h", "m", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "temp", "alpha", "id")
+    HALO_SYNC_FIELDS = ("x", "y", "z", "h", "m")
+    MAX_EXCHANGE_ARRAYS = 7
+
+    def __init__(self, sim, glob: dict, rank: int, nranks: int, device, pg=None, bucket: int = 64):
+        import torch
+
+        self.sim, self.L = sim, _cabi.load()
+        self.rank, self.nranks, self.pg, self.bucket = rank, nranks, pg, bucket
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.box_lim = [float(v) for v in glob["box"]]
+        self.boundary = [int(b) for b in glob["boundary"]]
+        self.p = glob["params"]
+        n = glob["x"].size
+        self.n_global = n
+        # initial distribution: a contiguous slice of the particles in GENERATION order; the first sync migrates them
+        b, e = rank * n // nranks, (rank + 1) * n // nranks
+        f = glob["fields"]
+
+        def chunk(name, dtype):
+            v = f.get(name, 0.0) if name not in ("x", "y", "z") else glob[name]
+            a = v[b:e] if isinstance(v, np.ndarray) and v.shape == (n,) else np.full(e - b, v)
+            return torch.from_numpy(np.ascontiguousarray(a, dtype)).to(self.dev)
+
+        self.cur = {k: chunk(k, np.float64 if k in ("x", "y", "z", "temp") else np.float32)
+                    for k in self.SYNC_FIELDS if k != "id"}
+        if "vx" in f:  # x_m1 = v * minDt (noh_init.hpp:99-101); zero for Sedov
+            for k, v in (("x_m1", "vx"), ("y_m1", "vy"), ("z_m1", "vz")):
+                self.cur[k] = (self.cur[v].double() * self.p.minDt).float()
+        self.cur["id"] = torch.arange(b, e, dtype=torch.int64, device=self.dev)
+        self.comm = init_comm(self.L, rank, nranks, device, pg)
+        self.hd = None
+        self.plan = None
+        self.result = _cabi.SphxStepResult()
+        self.conserved = _cabi.SphxConserved()
+        self.cons_scratch = torch.zeros(self.L.sphx_conserved_scratch_bytes(), dtype=torch.uint8, device=self.dev)
+        self.iteration = 0
+        self.timings = {}
+
+    # -- helpers ------------------------------------------------------------------------------------------------------
+    def _allreduce_host(self, values, op):
+        a = np.ascontiguousarray(values, np.float64)
+        if self.nranks > 1:
+            _cabi.check(self.L.sphx_allreduce_f64(self.comm, _p(a), a.size, op, None))
+        return a
+
+    def _sfc_sort(self, x, y, z, presorted=False, tree=None):
+        """keys (+ SFC permutation, + tree) of n particles through sphx_domain_sync"""
+        import torch
+        n = x.numel()
+        keys = torch.empty(n, dtype=torch.int64, device=self.dev)
+        order = torch.empty(n, dtype=torch.int32, device=self.dev)
+        max_nodes = tree.max_nodes if tree is not None else 0
+        scratch = torch.empty(self.L.sphx_domain_sync_bytes(n, max_nodes), dtype=torch.uint8, device=self.dev)
+        a = _cabi.SphxSyncArgs()
+        a.n, a.box, a.bucketSize = n, host.make_box(self.box_lim, self.boundary), self.bucket
+        a.x, a.y, a.z = x.data_ptr(), y.data_ptr(), z.data_ptr()
+        a.keys, a.order, a.maxNodes = keys.data_ptr(), order.data_ptr(), max_nodes
+        if tree is not None:
+            for k in ("prefixes", "childOffsets", "internalToLeaf", "levelRange", "leaves", "layout", "centers",
+                      "sizes"):
+                setattr(a, k, getattr(tree, k).data_ptr())
+        a.scratch, a.scratchBytes = scratch.data_ptr(), scratch.numel()
+        a.flags = (1 if presorted else 0) | (2 if tree is None else 0)
+        nn, nl = C.c_int(0), C.c_int(0)
+        rc = self.L.sphx_domain_sync(C.byref(a), None, C.byref(nn), C.byref(nl))
+        if tree is not None and rc == 0:
+            tree.num_nodes, tree.num_leaves = nn.value, nl.value
+        return rc, keys, order
+
+    def _reorder(self, order, src: dict, dst: dict, n: int):
+        names = list(src)
+        k = len(names)
+        _cabi.check(self.L.sphx_reorder_fields(order.data_ptr(), n, k,
+                                               (C.c_void_p * k)(*[src[m].data_ptr() for m in names]),
+                                               (C.c_void_p * k)(*[dst[m].data_ptr() for m in names]),
+                                               (C.c_int * k)(*[src[m].element_size() for m in names]), None))
+
+    # -- Domain::sync -------------------------------------------------------------------------------------------------
+    def sync(self):
+        import torch
+        import torch.distributed as dist
+
+        L, R, me = self.L, self.nranks, self.rank
+        cur = self.cur
+        n_old = cur["x"].numel()
+        # global box: open dimensions follow the particles (makeGlobalBox, box_mpi.hpp:66-109)
+        if any(b != 1 for b in self.boundary):
+            lo = [float(cur[k].min()) if n_old else np.inf for k in "xyz"]
+            hi = [float(cur[k].max()) if n_old else -np.inf for k in "xyz"]
+            lo, hi = self._allreduce_host(lo, 0), self._allreduce_host(hi, 1)
+            for d in range(3):
+                if self.boundary[d] != 1:
+                    self.box_lim[2 * d], self.box_lim[2 * d + 1] = float(lo[d]), float(hi[d])
+        h_max = float(self._allreduce_host([float(cur["h"].max()) if n_old else 0.0], 1)[0])
+        level = cell_level(self.box_lim, h_max)
+        ncell = 8 ** level
+
+        # 1. local SFC order, cell histogram, global histogram
+        rc, keys, order = self._sfc_sort(cur["x"], cur["y"], cur["z"])
+        _cabi.check(rc)
+        hist = torch.zeros(ncell, dtype=torch.int32, device=self.dev)
+        _cabi.check(L.sphx_cell_histogram(keys.data_ptr(), n_old, level, hist.data_ptr(), None))
+        local_counts = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+        if R > 1:
+            _cabi.check(L.sphx_allreduce_device(self.comm, hist.data_ptr(), ncell, 0, 2, None))
+        G = hist.cpu().numpy().view(np.uint32)
+
+        # 2. plan: assignment, halo cells, send lists, layout
+        cp = cell_plan(G, level, self.boundary, me, R)
+        sp = cp.cell_splits.astype(np.int64)
+        csum = np.concatenate([[0], np.cumsum(local_counts)])
+        send_off = csum[sp]  # my sorted particles [send_off[r], send_off[r+1]) belong to rank r
+        send_cnt = np.diff(send_off)
+        if R > 1:
+            allc = [None] * R
+            dist.all_gather_object(allc, send_cnt, group=self.pg)
+            recv_cnt = np.array([allc[q][me] for q in range(R)], np.int64)
+        else:
+            recv_cnt = send_cnt.copy()
+        recv_off = np.concatenate([[0], np.cumsum(recv_cnt)])
+        n_new = int(recv_off[-1])
+        assert n_new == cp.n_assigned, (n_new, cp.n_assigned)
+
+        # 3. migration: sort my particles, ship one slice per peer and field, merge-sort what arrived
+        sorted_ = {k: torch.empty_like(cur[k]) for k in self.SYNC_FIELDS}
+        self._reorder(order, cur, sorted_, n_old)
+        if R > 1:
+            arrived = {k: torch.empty(n_new, dtype=cur[k].dtype, device=self.dev) for k in self.SYNC_FIELDS}
+            so = np.ascontiguousarray(send_off, np.uint64)
+            ro = np.ascontiguousarray(recv_off, np.uint64)
+            names = list(self.SYNC_FIELDS)
+            k = len(names)
+            _cabi.check(L.sphx_exchange_slices(self.comm, _p(so), _p(ro), k,
+                                               (C.c_void_p * k)(*[sorted_[m].data_ptr() for m in names]),
+                                               (C.c_void_p * k)(*[arrived[m].data_ptr() for m in names]),
+                                               (C.c_int * k)(*[sorted_[m].element_size() for m in names]), None))
+            rc, _, order2 = self._sfc_sort(arrived["x"], arrived["y"], arrived["z"])
+            _cabi.check(rc)
+        else:
+            arrived, order2 = sorted_, None
+
+        # 4. local arrays [halos | assigned | halos]
+        n_local, first, last = cp.n_local, cp.n_halo_left, cp.n_halo_left + cp.n_assigned
+        if self.hd is None or n_local > self.cap_local or cp.n_assigned > self.cap_assigned:
+            self.cap_local, self.cap_assigned = int(1.2 * n_local) + 1024, int(1.2 * cp.n_assigned) + 1024
+            hd = self.sim.HydroData(self.cap_local, 0, self.cap_assigned, self.box_lim, self.boundary, self.p,
+                                    device=self.dev)
+            for name in ("x_m1", "y_m1", "z_m1", "du_m1"):
+                hd.f[name] = torch.zeros(self.cap_local, dtype=torch.float32, device=self.dev)
+            hd.f["id"] = torch.zeros(self.cap_local, dtype=torch.int64, device=self.dev)
+            hd.tree = self.sim.DeviceTree.empty(max(4096, self.cap_local // 4), self.dev)
+            self.hd = hd
+        hd = self.hd
+        hd.n, hd.first, hd.last = n_local, first, last
+        hd.box_lim = list(self.box_lim)
+        dstv = {k: hd.f[k][first:last] for k in self.SYNC_FIELDS}
+        if order2 is not None:
+            self._reorder(order2, arrived, dstv, n_new)
+        else:
+            for k in self.SYNC_FIELDS:
+                dstv[k].copy_(arrived[k])
+        self.cur = dstv  # views into the local arrays: integrate() updates them in place
+
+        # 5. halo plan on the device, halo exchange of the fields the search and the first loop read
+        self._send_idx = torch.from_numpy(cp.send_idx.view(np.int32).copy()).to(self.dev)
+        nsend = int(cp.send_offsets[-1]) if cp.send_offsets.size else 0
+        buf_bytes = self.MAX_EXCHANGE_ARRAYS * ((nsend * 8 + 15) // 16 * 16) + 64
+        self._send_buf = torch.empty(buf_bytes, dtype=torch.uint8, device=self.dev)
+        self._plan_host = cp  # keeps the host arrays alive
+        pl = _cabi.SphxHaloPlan()
+        pl.numPeers = cp.peers.size
+        pl.peers, pl.sendOffsets = cp.peers.ctypes.data, cp.send_offsets.ctypes.data
+        pl.sendIdx = self._send_idx.data_ptr()
+        pl.recvBegin, pl.recvCount = cp.recv_begin.ctypes.data, cp.recv_count.ctypes.data
+        pl.sendBuffer, pl.sendBufferBytes = self._send_buf.data_ptr(), buf_bytes
+        self.plan = pl
+        if R > 1:
+            self.exchange(list(self.HALO_SYNC_FIELDS))
+
+        # 6. octree over the local particles (already in SFC order)
+        while True:
+            rc, lkeys, _ = self._sfc_sort(hd.f["x"][:n_local], hd.f["y"][:n_local], hd.f["z"][:n_local], presorted=True,
+                                          tree=hd.tree)
+            if rc == 4 and hd.tree.max_nodes < 8 * n_local + 64:
+                hd.tree = self.sim.DeviceTree.empty(2 * hd.tree.max_nodes, self.dev)
+                continue
+            _cabi.check(rc)
+            break
+        self.local_keys = lkeys
+        self.level = level
+
+    def exchange(self, names):
+        arrs = (C.c_void_p * len(names))(*[self.hd.f[k].data_ptr() for k in names])
+        eb = (C.c_int * len(names))(*[self.hd.f[k].element_size() for k in names])
+        _cabi.check(self.L.sphx_halo_exchange(self.comm, C.byref(self.plan), len(names), arrs, eb, None))
+
+    # -- the rest of the loop ------------------------------------------------------------------------------------------
+    def compute_forces(self):
+        a = self.hd.args()
+        if self.nranks > 1:
+            _cabi.check(self.L.sphx_hydro_step_dist(C.byref(a), self.comm, C.byref(self.plan), C.byref(self.result)))
+        else:
+            _cabi.check(self.L.sphx_hydro_step(C.byref(a), None, None, C.byref(self.result)))
+        return self.result
+
+    def compute_conserved(self):
+        f, hd = self.hd.f, self.hd
+        _cabi.check(self.L.sphx_conserved_quantities(
+            f["x"].data_ptr(), f["y"].data_ptr(), f["z"].data_ptr(), f["vx"].data_ptr(), f["vy"].data_ptr(),
+            f["vz"].data_ptr(), f["m"].data_ptr(), f["temp"].data_ptr(), None, f["nc"].data_ptr(), hd.first, hd.last,
+            self.p.gamma, self.p.muiConst, 0.0, self.cons_scratch.data_ptr(),
+            self.comm if self.nranks > 1 else None, None, C.byref(self.conserved)))
+        return self.conserved
+
+    def integrate(self):
+        hd = self.hd
+        dt, dt1, tt = C.c_double(self.p.minDt), C.c_double(self.p.minDt_m1), C.c_double(self.p.ttot)
+        _cabi.check(self.L.sphx_compute_timestep(self.result.minDtCourant, self.result.minDtRho, self.p.maxDtIncrease,
+                                                 C.byref(dt), C.byref(dt1), C.byref(tt),
+                                                 self.comm if self.nranks > 1 else None, None))
+        self.p.minDt, self.p.minDt_m1, self.p.ttot = dt.value, dt1.value, tt.value
+        a = _cabi.SphxIntegrateArgs()
+        for k in _cabi.INTEGRATE_FIELDS:
+            setattr(a, k, hd.f[k].data_ptr() if k in hd.f else None)
+        a.first, a.last, a.box = hd.first, hd.last, host.make_box(self.box_lim, self.boundary)
+        a.dt, a.dt_m1, a.gamma, a.muiConst, a.ng0 = self.p.minDt, self.p.minDt_m1, self.p.gamma, self.p.muiConst, self.p.ng0
+        _cabi.check(self.L.sphx_integrate(C.byref(a)))
+
+    def step(self):
+        self.sync()
+        self.compute_forces()
+        c = self.compute_conserved()
+        row = (self.iteration, self.p.ttot, self.p.minDt, c.etot, c.ecin, c.eint, c.linmom, c.angmom, c.totalNeighbors)
+        self.integrate()
+        self.iteration += 1
+        return row
+
+    def assigned(self, name) -> np.ndarray:
+        a = self.hd.f[name][self.hd.first:self.hd.last].cpu().numpy()
+        return a.view(np.uint32) if name == "nc" else a
+
+    def close(self):
+        if self.comm:
+            self.L.sphx_comm_free(self.comm)
+            self.comm = C.c_void_p()

@@ -87,3 +87,105 @@ def test_multi_gpu_equals_single_gpu(world, name, side):
         np.testing.assert_allclose(s[1], dt_rho, rtol=1e-5)
         assert s[2] == ref_scal[0][2] and s[3] == ref_scal[0][3]
     assert sum(n_local) > ref["nc"].size  # halos are really there
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU time-step loop with the dynamic decomposition (DistributedSimulation.sync = multi-rank Domain::sync)
+# ---------------------------------------------------------------------------------------------------------------------
+SIM_FIELDS = ["x", "y", "z", "h", "vx", "vy", "vz", "temp", "alpha", "x_m1", "du_m1"]
+
+
+def _sim_worker(rank, world, port, name, side, steps, q):
+    import torch
+    import torch.distributed as dist
+    import sphexa_b200 as sx
+    from sphexa_b200 import dist as sdist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ds = sdist.DistributedSimulation(sx.sim, _case(name, side), rank, world, f"cuda:{rank}")
+        rows, stats = [], []
+        for _ in range(steps):
+            rows.append(ds.step())
+            stats.append((ds.hd.first, ds.hd.last - ds.hd.first, ds.hd.n, ds.level))
+        out = {k: ds.assigned(k) for k in SIM_FIELDS + ["nc"]}
+        out["id"] = ds.assigned("id")
+        out["rows"] = np.array(rows, np.float64)
+        out["stats"] = np.array(stats, np.int64)
+        out["keys_sorted"] = bool((ds.local_keys[1:] >= ds.local_keys[:-1]).all())
+        ds.close()
+        q.put((rank, out))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _run_sim(world, name, side, steps):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 27100 + (os.getpid() + 7 * world) % 1500
+    procs = [ctx.Process(target=_sim_worker, args=(r, world, port, name, side, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ids = np.concatenate([res[r]["id"] for r in range(world)])
+    assert np.array_equal(np.sort(ids), np.arange(ids.size))  # every particle on exactly one rank after migration
+    merged = {}
+    for k in SIM_FIELDS + ["nc"]:
+        v = np.concatenate([res[r][k] for r in range(world)])
+        full = np.zeros(ids.size, v.dtype)
+        full[ids] = v
+        merged[k] = full
+    return merged, res
+
+
+@pytest.mark.parametrize("name,side,steps", [("sedov", 30, 12), ("noh", 30, 12)])
+def test_single_rank_distributed_loop_equals_simulation(name, side, steps):
+    """world = 1: the dynamic-decomposition code path (histogram, plan, reorder, presorted tree) against
+    sim.Simulation, which sorts and builds its tree in one sphx_domain_sync call: identical bits"""
+    import sphexa_b200 as sx
+    from sphexa_b200 import cases
+    merged, res = _run_sim(1, name, side, steps)
+    s = getattr(cases, f"make_{name}_sim")(sx, side)
+    rows = np.array([s.step() for _ in range(steps)], np.float64)
+    np.testing.assert_array_equal(res[0]["rows"][:, 1:3], rows[:, 1:3])   # ttot, minDt
+    np.testing.assert_array_equal(res[0]["rows"][:, 8], rows[:, 8])       # total neighbours
+    np.testing.assert_allclose(res[0]["rows"][:, 3:6], rows[:, 3:6], rtol=1e-12)
+    assert res[0]["keys_sorted"]
+
+
+@pytest.mark.parametrize("name,side,steps", [("sedov", 30, 12), ("noh", 32, 12)])
+@pytest.mark.parametrize("world", [2])
+def test_multi_gpu_loop_equals_single_gpu(world, name, side, steps):
+    """N ranks re-decompose the domain in every step (migration + halo discovery + local tree) and advance the same
+    simulation as one rank: identical neighbour counts while the trajectories are bitwise comparable, energies and
+    the final per-particle state to fp32 summation-order noise."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ref, ref_res = _run_sim(1, name, side, steps)
+    got, res = _run_sim(world, name, side, steps)
+    r0, g0 = ref_res[0]["rows"], res[0]["rows"]
+    for r in range(1, world):
+        np.testing.assert_array_equal(res[r]["rows"], g0)              # every rank holds the reduced values
+    np.testing.assert_array_equal(g0[:3, 8], r0[:3, 8])                # total neighbours
+    np.testing.assert_allclose(g0[:, 8], r0[:, 8], rtol=1e-3)
+    np.testing.assert_allclose(g0[:, 2], r0[:, 2], rtol=1e-5)          # minDt
+    np.testing.assert_allclose(g0[:, 3], r0[:, 3], rtol=1e-6)          # etot
+    np.testing.assert_allclose(g0[:, 4], r0[:, 4], rtol=1e-4, atol=1e-12)  # ecin
+    for k in ("x", "y", "z"):
+        assert np.abs(got[k] - ref[k]).max() < 1e-7, k
+    np.testing.assert_allclose(got["h"], ref["h"], rtol=1e-6)
+    np.testing.assert_allclose(got["temp"], ref["temp"], rtol=1e-4)
+    assert all(res[r]["keys_sorted"] for r in range(world))
+    st = np.stack([res[r]["stats"] for r in range(world)])           # [rank, step, (first, nAssigned, nLocal, level)]
+    assert (st[:, :, 1].sum(0) == ref["x"].size).all()               # assigned counts always sum to N
+    assert (st[:, :, 2] > st[:, :, 1]).all()                          # halos are really there
+    imbalance = st[:, :, 1].max(0) / st[:, :, 1].mean(0)
+    assert imbalance.max() < 1.3
