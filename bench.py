@@ -203,6 +203,45 @@ def measure_next_rows(sx, cases, side, dev, peak, reps=5) -> dict:
     return out
 
 
+def measure_dist_loop(sx, sdist, glob, rank, world, dev, dist, reps=4) -> dict:
+    """N > 1: DistributedSimulation = the reference's whole main loop with the domain re-decomposed in every step
+    (global cell histogram over NCCL, migration, halo discovery, local tree). Times sync / forces / conserved /
+    integrate per step, max over ranks. Not part of `value` (SURVEY 8d: domain::sync is reported separately)."""
+    import torch
+    ds = sdist.DistributedSimulation(sx.sim, glob, rank, world, dev)
+    ds.step()
+    ds.step()
+    torch.cuda.synchronize()
+    names = ["domain_sync", "hydro_step", "conserved", "integrate"]
+    acc = torch.zeros(len(names), dtype=torch.float64, device=dev)
+    for _ in range(reps):
+        dist.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        ds.sync()
+        ev[1].record()
+        ds.compute_forces()
+        ev[2].record()
+        ds.compute_conserved()
+        ev[3].record()
+        ds.integrate()
+        ev[4].record()
+        torch.cuda.synchronize()
+        acc += torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(4)], dtype=torch.float64, device=dev) / reps
+    dist.all_reduce(acc, op=dist.ReduceOp.MAX)
+    sizes = torch.tensor([ds.hd.last - ds.hd.first, ds.hd.n], dtype=torch.int64, device=dev)
+    smax = sizes.clone()
+    dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+    out = {"ms": dict(zip(names, acc.tolist())), "loop_ms_per_step": float(acc.sum()),
+           "particles_per_sec_whole_loop": ds.n_global / (float(acc.sum()) * 1e-3),
+           "cell_level": ds.level, "max_assigned_per_rank": int(smax[0]), "max_local_per_rank": int(smax[1]),
+           "note": "dynamic SFC decomposition redone every step: device histogram + ncclAllReduce, host plan, slice "
+                   "migration (ncclSend/Recv), merge sort, halo exchange of x,y,z,h,m, local octree; includes the host "
+                   "plan and the D2H/H2D of the 8^level-cell histogram"}
+    ds.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -237,7 +276,8 @@ def our_arm(args):
         hd = cases.make_sedov(sx, side, device=dev)
         n_assigned = hd.n
     else:
-        dh = sdist.DistributedHydro(sx.sim, cases.sedov_global(side), rank, world, dev)
+        glob = cases.sedov_global(side)
+        dh = sdist.DistributedHydro(sx.sim, glob, rank, world, dev)
         hd = dh.hd
         n_assigned = dh.n_assigned
     setup_s = time.time() - t0
@@ -377,6 +417,14 @@ def our_arm(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = n_global / (float(e2e_ms.item()) * 1e-3)
 
+    # ---- N > 1: the dynamic decomposition (multi-rank Domain::sync) and the whole loop, reported separately ---------
+    dist_rows = None
+    if world > 1 and not args.no_next_rows:
+        try:
+            dist_rows = measure_dist_loop(sx, sdist, glob, rank, world, dev, dist)
+        except Exception as e:  # noqa: BLE001
+            dist_rows = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -450,7 +498,7 @@ def our_arm(args):
                       "candidates_per_block_mean": float(bs["numCand"].mean()),
                       "candidates_per_block_max": int(bs["numCand"].max()),
                       "candidates_per_particle": bs["candTop"] / n, "fold_blocks": int((bs["flags"] & 1).sum())},
-            "next_rows": next_rows, "setup_s": setup_s}
+            "next_rows": next_rows if world == 1 else dist_rows, "setup_s": setup_s}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
