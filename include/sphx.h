@@ -384,6 +384,60 @@ extern "C"
                                   const unsigned* nc, size_t first, size_t last, double gamma, float muiConst,
                                   double egrav, void* scratch, struct SphxComm* comm, void* stream, SphxConserved* out);
 
+    /* --- turbulence stirring ---------------------------------------------------------------------- */
+
+    /* the keys of sphexa::TurbulenceConstants() (main/src/init/turbulence_init.hpp:47-72) that
+     * sph::TurbulenceData::initModes reads (sph/include/sph/hydro_turb/turbulence_data.hpp:143-177) */
+    typedef struct SphxTurbulenceSettings
+    {
+        double   solWeight;      /* 0.5 */
+        double   Lbox;           /* 1.0 */
+        double   stEnergyPrefac; /* 5e-3 */
+        double   stMachVelocity; /* 0.3 */
+        double   epsilon;        /* 1e-15 */
+        double   powerLawExp;    /* 5/3 */
+        double   anglesExp;      /* 2 */
+        uint64_t stMaxModes;     /* 100000 */
+        uint64_t rngSeed;        /* 251299 */
+        int      stSpectForm;    /* 0 band, 1 parabola, 2 power law */
+    } SphxTurbulenceSettings;
+
+    /* sph::TurbulenceData<double, GpuTag> (turbulence_data.hpp:46-180): the stirring modes and amplitudes
+     * (createStirringModes, create_modes.hpp:33-227), the Ornstein-Uhlenbeck phases and the std::mt19937 that drives
+     * them. Host state plus small device tables; the device tables are created by the first sphx_drive_turbulence. */
+    typedef struct SphxTurbulence SphxTurbulence;
+    int  sphx_turbulence_create(const SphxTurbulenceSettings* s, SphxTurbulence** out);
+    void sphx_turbulence_free(SphxTurbulence* t);
+    /* sizes[0] numModes, [1] 1 if every mode is an integer multiple (|i| <= 15) of 2 pi / Lbox (lattice kernel),
+     * [2] largest |i|, [3] bytes of the text form of the random engine (incl. the terminating 0) */
+    void sphx_turbulence_sizes(const SphxTurbulence* t, size_t sizes[4]);
+    /* copy out the host state (any pointer may be NULL): modes[3 numModes], amplitudes[numModes], phases[6 numModes],
+     * phasesReal[3 numModes], phasesImag[3 numModes], scalars[4] = variance, decayTime, solWeight, solWeightNorm,
+     * rngState = text form of the engine (operator<< of std::mt19937, what TurbulenceData::loadOrStore writes) */
+    void sphx_turbulence_get(const SphxTurbulence* t, double* modes, double* amplitudes, double* phases,
+                             double* phasesReal, double* phasesImag, double* scalars, char* rngState);
+    /* restart (TurbulenceData::loadOrStore, turbulence_data.hpp:82-115): replace the state by stored values. Any pointer
+     * may be NULL (that part is kept). modes/amplitudes (3 numModes / numModes values) replace the mode set; phases then
+     * must be given too (6 numModes). scalars[4] as in sphx_turbulence_get. rngState: text form of the engine. */
+    int sphx_turbulence_restore(SphxTurbulence* t, size_t numModes, const double* modes, const double* amplitudes,
+                                const double* phases, const double* scalars, const char* rngState);
+
+    /* host only: one Ornstein-Uhlenbeck step of the phases over minDt (updateNoise, driver.hpp:85-98) and their
+     * projection to phasesReal / phasesImag (computePhases, phases.hpp:46-72): the first half of driveTurbulence */
+    int sphx_turbulence_advance_host(SphxTurbulence* t, double minDt);
+
+    /* sph::driveTurbulence (sph/include/sph/hydro_turb/driver.hpp:102-128): advance the OU phases by minDt
+     * (updateNoise :85-98), project them (computePhases, phases.hpp:46-72), upload, and add the stirring accelerations
+     * of particles [first, last) to ax, ay, az (computeStirringGpu, stirring_gpu.cu:43-74; stirParticle,
+     * stirring.hpp:45-83). Called right after sphx_hydro_step, as TurbVeProp::computeForces does (turb_ve.hpp:67-72).
+     * Enqueued on the stream; does not synchronise. */
+    int sphx_drive_turbulence(SphxTurbulence* t, const double* x, const double* y, const double* z, float* ax,
+                              float* ay, float* az, size_t first, size_t last, double minDt, void* stream);
+    /* the second half only (no OU update): accelerations from the current phasesReal / phasesImag
+     * (computeStirringGpu) */
+    int sphx_compute_stirring(SphxTurbulence* t, const double* x, const double* y, const double* z, float* ax,
+                              float* ay, float* az, size_t first, size_t last, void* stream);
+
     /* --- SFC domain decomposition over the GPUs of one node (host side) --------------------------------- */
 
     /* cstone::makeSfcAssignment / uniformBins (domain/include/cstone/domain/domaindecomp.hpp:33-110): contiguous

@@ -10,7 +10,11 @@
  *   (main/src/propagator/ve_hydro.hpp:130-215) including the release/acquire aliasing, with a snapshot of every
  *   output right after the stage that produces it (gradh, divv, curlv are recycled before computeForces returns).
  *
- * Usage: ref_harness <case> <n> <steps> <outdir> [dumpEvery=1] [dumpNeighbors=1] [hscale=1] [avClean=0]
+ * Usage: ref_harness <case> <n> <steps> <outdir> [dumpEvery=1] [dumpNeighbors=1] [hscale=1] [avClean=0] [stir=0]
+ *   stir=1|2 (case turb only): the reference's turbulence-ve propagator (main/src/propagator/turb_ve.hpp:67-72):
+ *   particles start at rest, sph::driveTurbulence runs after computeMomentumEnergy; 1 = TurbulenceConstants() as they
+ *   are (parabolic spectrum), 2 = stSpectForm 2 (power law, modes drawn from the random engine). Dumps the
+ *   TurbulenceData state and the accelerations after stirring (stir_ax, stir_ay, stir_az).
  *   avClean=1 runs HydroVeProp<true,...>: dV11..dV33 active (ve_hydro.hpp:78-83), computeMomentumEnergy<true>
  *   hscale != 1 perturbs the initial smoothing lengths (h*=hscale if id%3==0, h/=hscale if id%3==1) so that the
  *   coupled h / neighbour-count iteration of sph/find_neighbors.hpp:17-36 is exercised in both directions
@@ -39,6 +43,7 @@
 #include "init/noh_init.hpp"
 #include "init/turbulence_init.hpp"
 #include "observables/conserved_quantities.hpp"
+#include "sph/hydro_turb/driver.hpp"
 
 using namespace sphexa;
 using namespace sph;
@@ -127,6 +132,9 @@ int main(int argc, char** argv)
     bool        dumpNb    = argc > 6 ? std::stoi(argv[6]) != 0 : true;
     double      hscale    = argc > 7 ? std::stod(argv[7]) : 1.0;
     bool        avClean   = argc > 8 ? std::stoi(argv[8]) != 0 : false;
+    int         stir      = argc > 9 ? std::stoi(argv[9]) : 0;
+
+    std::unique_ptr<sph::TurbulenceData<double, cstone::CpuTag>> turb;
 
     MPI_Init(&argc, &argv);
     fs::create_directories(outDir);
@@ -186,9 +194,14 @@ int main(int argc, char** argv)
         else
         {
             initTurbulenceHydroFields(d, settings);
-            // stirring is out of scope: impose a deterministic subsonic solenoidal velocity field
+            if (stir)
+            {
+                if (stir == 2) { settings["stSpectForm"] = 2; }
+                turb = std::make_unique<sph::TurbulenceData<double, cstone::CpuTag>>(settings, false);
+            }
+            // without stirring: impose a deterministic subsonic solenoidal velocity field
             double cs = std::sqrt(d.gamma * (d.gamma - 1.0) * settings.at("u0"));
-            for (size_t i = 0; i < d.x.size(); ++i)
+            for (size_t i = 0; i < d.x.size() && !stir; ++i)
             {
                 d.vx[i]   = 0.3 * cs * std::sin(2 * M_PI * d.y[i]);
                 d.vy[i]   = 0.3 * cs * std::sin(2 * M_PI * d.z[i]);
@@ -386,6 +399,25 @@ int main(int argc, char** argv)
             dump->put("du", d.du, first, last);
             double dts[2] = {d.minDtCourant, d.minDtRho};
             dump->put("dts", dts, 2);
+        }
+
+        if (turb)
+        {
+            if (doDump && step == 0) { dump->put("turb_phases_in", turb->phases.data(), turb->phases.size()); }
+            driveTurbulence(groups.view(), d, *turb);
+            if (doDump)
+            {
+                dump->put("stir_ax", d.ax, first, last);
+                dump->put("stir_ay", d.ay, first, last);
+                dump->put("stir_az", d.az, first, last);
+                dump->put("turb_modes", turb->modes.data(), turb->modes.size());
+                dump->put("turb_amplitudes", turb->amplitudes.data(), turb->amplitudes.size());
+                dump->put("turb_phases", turb->phases.data(), turb->phases.size());
+                dump->put("turb_phasesReal", turb->phasesReal.data(), turb->phasesReal.size());
+                dump->put("turb_phasesImag", turb->phasesImag.data(), turb->phasesImag.size());
+                double sc[4] = {turb->variance, turb->decayTime, turb->solWeight, turb->solWeightNorm};
+                dump->put("turb_scalars", sc, 4);
+            }
         }
 
         computeConservedQuantities(first, last, d, MPI_COMM_WORLD);

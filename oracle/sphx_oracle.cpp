@@ -961,4 +961,73 @@ void orc_momentum_energy_jloop_d(int avClean, unsigned i, double K, const OrcBox
     out[0] = a[0], out[1] = a[1], out[2] = a[2], out[3] = du, out[4] = mv;
 }
 
+/* --- turbulence stirring ------------------------------------------------------------------------------------------- */
+
+// stirring.hpp:106-125 (loop over the groups' particles) with stirParticle :45-83; Tc = T = double, Ta = float
+void orc_compute_stirring(unsigned first, unsigned last, const double* x, const double* y, const double* z, float* ax,
+                          float* ay, float* az, unsigned numModes, const double* modes, const double* phaseReal,
+                          const double* phaseImag, const double* amplitudes, double solWeightNorm)
+{
+#pragma omp parallel for schedule(static)
+    for (unsigned i = first; i < last; ++i)
+    {
+        float sum[3] = {0.f, 0.f, 0.f}; // Ta turbAx = 0.0 ...
+        for (unsigned m = 0; m < numModes; ++m)
+        {
+            const double* k = modes + 3 * m;
+            // stirring.hpp:56-63: z first, then y, then x
+            double cz = std::cos(k[2] * z[i]), sz = std::sin(k[2] * z[i]);
+            double cy = std::cos(k[1] * y[i]), sy = std::sin(k[1] * y[i]);
+            double cx = std::cos(k[0] * x[i]), sx = std::sin(k[0] * x[i]);
+            // real and imaginary part of exp(i k.x) (:68-72)
+            double re = (cx * cy - sx * sy) * cz - (sx * cy + cx * sy) * sz;
+            double im = cx * (cy * sz + sy * cz) + sx * (cy * cz - sy * sz);
+            for (int d = 0; d < 3; ++d)
+            {
+                // Ta += double expression (:74-76): added in double, rounded to float
+                sum[d] = float(double(sum[d]) + amplitudes[m] * (phaseReal[3 * m + d] * re - phaseImag[3 * m + d] * im));
+            }
+        }
+        ax[i] = float(double(ax[i]) + solWeightNorm * double(sum[0])); // :118-120
+        ay[i] = float(double(ay[i]) + solWeightNorm * double(sum[1]));
+        az[i] = float(double(az[i]) + solWeightNorm * double(sum[2]));
+    }
+}
+
+// phases.hpp:46-72
+void orc_compute_phases(unsigned numModes, const double* ou, double solWeight, const double* modes, double* phasesReal,
+                        double* phasesImag)
+{
+    for (unsigned i = 0; i < numModes; ++i)
+    {
+        double ka = 0.0, kb = 0.0, kk = 0.0;
+        for (int j = 0; j < 3; ++j)
+        {
+            kk = kk + modes[3 * i + j] * modes[3 * i + j];
+            ka = ka + modes[3 * i + j] * ou[6 * i + 2 * j + 1];
+            kb = kb + modes[3 * i + j] * ou[6 * i + 2 * j];
+        }
+        for (int j = 0; j < 3; ++j)
+        {
+            double diva  = modes[3 * i + j] * ka / kk;
+            double divb  = modes[3 * i + j] * kb / kk;
+            double curla = ou[6 * i + 2 * j] - divb;
+            double curlb = ou[6 * i + 2 * j + 1] - diva;
+            phasesReal[3 * i + j] = solWeight * curla + (1.0 - solWeight) * divb;
+            phasesImag[3 * i + j] = solWeight * curlb + (1.0 - solWeight) * diva;
+        }
+    }
+}
+
+// driver.hpp:85-98 with the Gaussian deviates given
+void orc_update_noise(unsigned n, double* phases, double stddev, double dt, double ts, const double* gaussians)
+{
+    double dampingA = std::exp(-dt / ts);
+    double dampingB = std::sqrt(1.0 - dampingA * dampingA);
+    for (unsigned i = 0; i < n; ++i)
+    {
+        phases[i] = phases[i] * dampingA + stddev * dampingB * gaussians[i];
+    }
+}
+
 } // extern "C"

@@ -133,6 +133,19 @@ extern "C"
                                        const double* dV13, const double* dV22, const double* dV23, const double* dV33,
                                        double* out /* ax ay az du maxvsignal */);
 
+    /* --- turbulence stirring (sph/include/sph/hydro_turb/) ----------------------------------------------------------- */
+    /* sph::computeStirring (stirring.hpp:106-125) with stirParticle (:45-83), Tc = T = double, Ta = float */
+    void orc_compute_stirring(unsigned first, unsigned last, const double* x, const double* y, const double* z,
+                              float* ax, float* ay, float* az, unsigned numModes, const double* modes,
+                              const double* phaseReal, const double* phaseImag, const double* amplitudes,
+                              double solWeightNorm);
+    /* sph::computePhases (phases.hpp:46-72), numDim = 3 */
+    void orc_compute_phases(unsigned numModes, const double* ouPhases, double solWeight, const double* modes,
+                            double* phasesReal, double* phasesImag);
+    /* the deterministic part of sph::updateNoise (driver.hpp:85-98): phases = phases * f + stddev * sqrt(1 - f^2) * z
+     * for given unit Gaussians z[] (the reference draws them from std::normal_distribution<double>(0,1)) */
+    void orc_update_noise(unsigned n, double* phases, double stddev, double dt, double ts, const double* gaussians);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,20 @@ class SphxConserved(C.Structure):
                 ("angmom3", C.c_double * 3), ("totalNeighbors", C.c_ulong)]
 
 
+class SphxTurbulenceSettings(C.Structure):
+    """defaults = sphexa::TurbulenceConstants() (main/src/init/turbulence_init.hpp:47-72)"""
+    _fields_ = [("solWeight", C.c_double), ("Lbox", C.c_double), ("stEnergyPrefac", C.c_double),
+                ("stMachVelocity", C.c_double), ("epsilon", C.c_double), ("powerLawExp", C.c_double),
+                ("anglesExp", C.c_double), ("stMaxModes", C.c_uint64), ("rngSeed", C.c_uint64),
+                ("stSpectForm", C.c_int)]
+
+    def __init__(self, **kw):
+        d = dict(solWeight=0.5, Lbox=1.0, stEnergyPrefac=5.0e-3, stMachVelocity=0.3, epsilon=1e-15,
+                 powerLawExp=5.0 / 3, anglesExp=2.0, stMaxModes=100000, rngSeed=251299, stSpectForm=1)
+        d.update(kw)
+        super().__init__(**d)
+
+
 UNIQUE_ID_BYTES = 128
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
@@ -95,7 +109,8 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_allreduce_device", "sphx_exchange_slices", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get",
            "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
-           "sphx_conserved_quantities"]
+           "sphx_conserved_quantities", "sphx_turbulence_create", "sphx_turbulence_free", "sphx_turbulence_sizes",
+           "sphx_turbulence_get", "sphx_turbulence_restore", "sphx_turbulence_advance_host", "sphx_drive_turbulence", "sphx_compute_stirring"]
 
 
 class SphxError(RuntimeError):
@@ -170,6 +185,18 @@ def load():
     L.sphx_conserved_quantities.argtypes = [C.c_void_p] * 10 + [C.c_size_t, C.c_size_t, C.c_double, C.c_float,
                                                                  C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                                                  C.c_void_p]
+    L.sphx_turbulence_create.argtypes = [C.c_void_p, C.c_void_p]
+    L.sphx_turbulence_free.argtypes = [C.c_void_p]
+    L.sphx_turbulence_free.restype = None
+    L.sphx_turbulence_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.sphx_turbulence_sizes.restype = None
+    L.sphx_turbulence_get.argtypes = [C.c_void_p] * 8
+    L.sphx_turbulence_get.restype = None
+    L.sphx_turbulence_restore.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_char_p]
+    L.sphx_turbulence_advance_host.argtypes = [C.c_void_p, C.c_double]
+    L.sphx_drive_turbulence.argtypes = [C.c_void_p] * 7 + [C.c_size_t, C.c_size_t, C.c_double, C.c_void_p]
+    L.sphx_compute_stirring.argtypes = [C.c_void_p] * 7 + [C.c_size_t, C.c_size_t, C.c_void_p]
     _lib = L
     return L
 

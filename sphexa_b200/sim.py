@@ -241,6 +241,73 @@ class HydroData:
         return self.export_neighbors_device().cpu().numpy().view(np.uint32)
 
 
+class Turbulence:
+    """sph::TurbulenceData + sph::driveTurbulence (sph/include/sph/hydro_turb/turbulence_data.hpp, driver.hpp:102-128)
+    behind sphx_turbulence_* / sphx_drive_turbulence: host state (modes, OU phases, std::mt19937) and device tables
+    live in libsphx."""
+
+    def __init__(self, **settings):
+        self.L = _cabi.load()
+        s = _cabi.SphxTurbulenceSettings(**settings)
+        self.handle = C.c_void_p()
+        _cabi.check(self.L.sphx_turbulence_create(C.byref(s), C.byref(self.handle)))
+        sz = (C.c_size_t * 4)()
+        self.L.sphx_turbulence_sizes(self.handle, sz)
+        self.num_modes, self.lattice, self.max_index, self._rng_bytes = int(sz[0]), bool(sz[1]), int(sz[2]), int(sz[3])
+
+    def state(self) -> dict:
+        nm = self.num_modes
+        out = dict(modes=np.zeros(3 * nm), amplitudes=np.zeros(nm), phases=np.zeros(6 * nm), phasesReal=np.zeros(3 * nm),
+                   phasesImag=np.zeros(3 * nm), scalars=np.zeros(4))
+        sz = (C.c_size_t * 4)()
+        self.L.sphx_turbulence_sizes(self.handle, sz)
+        rng = C.create_string_buffer(int(sz[3]))
+        self.L.sphx_turbulence_get(self.handle, *[out[k].ctypes.data for k in ("modes", "amplitudes", "phases",
+                                                                                "phasesReal", "phasesImag", "scalars")],
+                                   C.cast(rng, C.c_void_p))
+        out["rng"] = rng.value.decode()
+        return out
+
+    def restore(self, phases=None, rng: str | None = None, modes=None, amplitudes=None, scalars=None):
+        """TurbulenceData::loadOrStore: replace (parts of) the state"""
+        arr = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)  # noqa: E731
+        ph, mo, am, sc = arr(phases), arr(modes), arr(amplitudes), arr(scalars)
+        nm = am.size if am is not None else self.num_modes
+        ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        _cabi.check(self.L.sphx_turbulence_restore(self.handle, nm, ptr(mo), ptr(am), ptr(ph), ptr(sc),
+                                                   rng.encode() if rng is not None else None))
+        sz = (C.c_size_t * 4)()
+        self.L.sphx_turbulence_sizes(self.handle, sz)
+        self.num_modes, self.lattice, self.max_index = int(sz[0]), bool(sz[1]), int(sz[2])
+
+    def advance_host(self, min_dt: float):
+        """updateNoise + computePhases (host half of driveTurbulence)"""
+        _cabi.check(self.L.sphx_turbulence_advance_host(self.handle, min_dt))
+
+    def drive(self, hd: "HydroData", min_dt: float):
+        f = hd.f
+        _cabi.check(self.L.sphx_drive_turbulence(self.handle, f["x"].data_ptr(), f["y"].data_ptr(), f["z"].data_ptr(),
+                                                 f["ax"].data_ptr(), f["ay"].data_ptr(), f["az"].data_ptr(), hd.first,
+                                                 hd.last, min_dt, hd.stream.cuda_stream if hd.stream is not None else None))
+
+    def compute_stirring(self, hd: "HydroData"):
+        f = hd.f
+        _cabi.check(self.L.sphx_compute_stirring(self.handle, f["x"].data_ptr(), f["y"].data_ptr(), f["z"].data_ptr(),
+                                                 f["ax"].data_ptr(), f["ay"].data_ptr(), f["az"].data_ptr(), hd.first,
+                                                 hd.last, hd.stream.cuda_stream if hd.stream is not None else None))
+
+    def close(self):
+        if self.handle:
+            self.L.sphx_turbulence_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class Simulation(HydroData):
     """One rank of the reference's time-step loop (main/src/sphexa/sphexa.cpp:141-170 with HydroVeProp,
     main/src/propagator/ve_hydro.hpp:114-215), every stage a libsphx call on device-resident fields:
@@ -264,6 +331,8 @@ class Simulation(HydroData):
         self.cons_scratch = torch.zeros(self.L.sphx_conserved_scratch_bytes(), dtype=torch.uint8, device=dev)
         self.conserved = _cabi.SphxConserved()
         self.iteration = 0
+        #: set to a Turbulence to run the reference's turbulence-ve propagator (TurbVeProp, turb_ve.hpp:67-72)
+        self.turbulence: Turbulence | None = None
 
     def _alloc_tree(self, max_nodes: int):
         self.tree = DeviceTree.empty(max_nodes, self.device)
@@ -300,8 +369,12 @@ class Simulation(HydroData):
             self.f[k], self.spare[k] = self.spare[k], self.f[k]
 
     def compute_forces(self):
-        """HydroVeProp::computeForces after sync (ve_hydro.hpp:130-204)"""
-        return self.hydro_step()
+        """HydroVeProp::computeForces after sync (ve_hydro.hpp:130-204); with `turbulence` set, TurbVeProp::computeForces
+        (turb_ve.hpp:67-72): the same followed by driveTurbulence"""
+        r = self.hydro_step()
+        if self.turbulence is not None:
+            self.turbulence.drive(self, self.p.minDt)
+        return r
 
     def compute_conserved(self) -> _cabi.SphxConserved:
         f = self.f

@@ -14,6 +14,11 @@ Outputs (committed):
   sedov50_energies.npz  the same over 100 steps of BASELINE config 0 (sedov -n 50)
   noh14_energies.npz, turb12_energies.npz  40 steps continuing noh14_step0 / turb12_step0 (open box that follows the
                         particles; periodic box with a velocity field)
+  turb12s_step0.npz, turb12s_step2.npz  the reference's turbulence-ve propagator (ref_harness stir=1: particles at rest,
+                        sph::driveTurbulence after the momentum loop): inputs, loop outputs, TurbulenceData state,
+                        accelerations after stirring; no neighbour lists / tree (the test builds its own)
+  turb12s_energies.npz  40 steps of the same
+  turb_form2.npz        TurbulenceData state for stSpectForm = 2 (modes drawn from the random engine)
 """
 import subprocess
 import sys
@@ -94,8 +99,26 @@ def make_steps():
             np.savez_compressed(GOLDEN / f"{tag}_energies.npz", series=np.loadtxt(out / "energies.txt"), columns=cols)
 
 
+def make_stirring():
+    cols = np.array("step ttot minDt etot ecin eint linmom angmom totalNeighbors".split())
+    with tempfile.TemporaryDirectory() as tmp:
+        dumps = run_ref_harness("turb", 12, 3, Path(tmp) / "s", dump_neighbors=False, stir=1)
+        for k in (0, 2):
+            d = {key: v for key, v in dumps[k].items() if not key.startswith("tree_") and key not in ("wh", "whd", "_step")}
+            np.savez_compressed(GOLDEN / f"turb12s_step{k}.npz", **d)
+        out = Path(tmp) / "e"
+        run_ref_harness("turb", 12, 40, out, dump_every=100000, dump_neighbors=False, stir=1)
+        np.savez_compressed(GOLDEN / "turb12s_energies.npz", series=np.loadtxt(out / "energies.txt"), columns=cols)
+        d = run_ref_harness("turb", 6, 1, Path(tmp) / "f2", dump_neighbors=False, stir=2)[0]
+        np.savez_compressed(GOLDEN / "turb_form2.npz", **{k: v for k, v in d.items() if k.startswith("turb_")})
+
+
 if __name__ == "__main__":
-    make_kat()
-    make_steps()
+    if len(sys.argv) > 1 and sys.argv[1] == "stirring":
+        make_stirring()
+    else:
+        make_kat()
+        make_steps()
+        make_stirring()
     for f in sorted(GOLDEN.glob("*.npz")):
         print(f.name, f.stat().st_size)

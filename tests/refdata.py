@@ -39,14 +39,16 @@ def have_ref_harness() -> bool:
 
 
 def run_ref_harness(case: str, n: int, steps: int, outdir, dump_every: int = 1, dump_neighbors: bool = True,
-                    threads: int | None = None, hscale: float = 1.0, av_clean: bool = False) -> list[dict]:
+                    threads: int | None = None, hscale: float = 1.0, av_clean: bool = False,
+                    stir: int = 0) -> list[dict]:
     """Run the compiled reference (oracle/_ref/ref_harness) and return one dict per dumped step."""
     outdir = Path(outdir)
     env = dict(os.environ)
     if threads:
         env["OMP_NUM_THREADS"] = str(threads)
     subprocess.run([str(REF_HARNESS), case, str(n), str(steps), str(outdir), str(dump_every),
-                    "1" if dump_neighbors else "0", repr(float(hscale)), "1" if av_clean else "0"], check=True, env=env,
+                    "1" if dump_neighbors else "0", repr(float(hscale)), "1" if av_clean else "0", str(int(stir))], check=True,
+                   env=env,
                    stdout=subprocess.PIPE)
     steps_out = []
     k = 0
