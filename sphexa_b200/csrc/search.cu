@@ -37,6 +37,10 @@ constexpr int kMaxWords      = 768;  // provisional numbering: 32 slots per word
 constexpr int kMaxTiles      = 48;
 constexpr int kFrontierCap   = 1024; // nodes per tree level that overlap the block's bounding box
 constexpr int kWordsPerThread = kMaxWords / kSearchThreads;
+constexpr unsigned kDecodeAhead = 6;  // list decode: hit-mask rows prefetched into L1 ahead of their use
+constexpr int kTileQuads      = kTileCap / 4;
+constexpr int kKeepWords      = kTileQuads / 32;
+static_assert(kTileQuads % 32 == 0, "quad cull: whole ballots per tile");
 static_assert(kMaxWords % kSearchThreads == 0, "prefix sum: a fixed number of words per thread");
 
 struct SearchShared
@@ -51,12 +55,17 @@ struct SearchShared
     int            leafFirst[kMaxLeaves]; // first particle of the sorted leaf
     unsigned short leafW0[kMaxLeaves];    // first provisional word of the leaf
     unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
-    float          leafBox[kMaxLeaves * 6];
+    // boxes of the staged quads (four SFC-consecutive particles of a leaf) of the current tile, relative to the block
+    // origin: [lo x | lo y | lo z | hi x | hi y | hi z][kTileQuads]. Aliased by scratch of the tree walk.
+    float          quadBox[6 * kTileQuads];
+    unsigned       keep[kSearchWarps][kKeepWords];     // per warp: quads of the tile within reach of its targets
+    unsigned short quadMeta[kTileQuads];               // provisional word of the quad << 3 | position in the word
     int            tileFirstLeaf[kMaxTiles + 1];
     double         red[6 * kSearchWarps];
     int            count[2];
     int            nLeaf, nTiles, err, wEnd;
     int            maxLeafHalf[3];
+    int            maxLeafCount; // most particles in one of the block's leaves
     int            scan[kSearchWarps];
     int            selfP[kSearchThreads]; // provisional slot of each target's own particle
     unsigned       candBegin, numCand, nextBlock;
@@ -128,10 +137,10 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
 {
     // scratch of the tree walk, aliased onto arrays that are written only later:
     int* frontier = reinterpret_cast<int*>(s.tileX);    // [2][kFrontierCap]: until the first tile is staged
-    int* leafNode = reinterpret_cast<int*>(s.leafBox);  // leaves in traversal order: until they are ranked
+    int* leafNode = reinterpret_cast<int*>(s.quadBox);  // leaves in traversal order: until they are ranked
     int* leafTmp  = reinterpret_cast<int*>(s.usedBits); // node index of the ranked leaves: until the leaf boxes exist
     static_assert(2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX), "frontier scratch");
-    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.leafBox), "leaf scratch");
+    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.quadBox), "leaf scratch");
     static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.usedBits), "ranked-leaf scratch");
     static_assert(offsetof(SearchShared, tileY) == offsetof(SearchShared, tileX) + sizeof(s.tileX) &&
                       offsetof(SearchShared, tileZ) == offsetof(SearchShared, tileY) + sizeof(s.tileY),
@@ -163,8 +172,8 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     // only if the search sphere of at least one target touches its box. This plays the role of the reference's group
     // splits (computeGroupSplits, traversal/groups_gpu.cu:106-135), which keep a group's bounding box small.
     bool    precise = false;
-    float4* tgtSph  = reinterpret_cast<float4*>(s.leafBox + kMaxLeaves); // [T], live during the walk only
-    static_assert((kMaxLeaves + 4 * kBlockTargets) * sizeof(float) <= sizeof(s.leafBox), "target sphere scratch");
+    float4* tgtSph  = reinterpret_cast<float4*>(s.quadBox + kMaxLeaves); // [T], live during the walk only
+    static_assert((kMaxLeaves + 4 * kBlockTargets) * sizeof(float) <= sizeof(s.quadBox), "target sphere scratch");
 
     for (;;)
     {
@@ -204,6 +213,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             s.count[0] = 1, s.count[1] = 0;
             s.nLeaf = 0, s.err = 0;
             s.maxLeafHalf[0] = s.maxLeafHalf[1] = s.maxLeafHalf[2] = 0;
+            s.maxLeafCount = 0;
             frontier[0] = 0; // root
         }
         __syncthreads();
@@ -336,6 +346,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
 #pragma unroll
             for (int d = 0; d < 3; ++d)
                 atomicMax(&s.maxLeafHalf[d], __float_as_int(__double2float_ru(a.tree.sizes[3 * node + d])));
+            atomicMax(&s.maxLeafCount, int(e - b));
         }
         __syncthreads();
 
@@ -352,30 +363,76 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         }
         const float E = __double2float_ru(fmax(ex, fmax(ey, ez))) * 1.0001f;
 
-        // leaf boxes relative to the block origin (for the per-warp cull)
-        for (int q = t; q < L; q += T)
+        // provisional numbering (every leaf starts a new 32-slot word) and tiles. With P = running sum of the leaves'
+        // particle counts (each padded to a multiple of four), leaf q is staged in tile P[q] / B at offset P[q] % B:
+        // B = kTileCap - largest padded count, so no leaf crosses the end of the tile buffer and no tile index is
+        // skipped; the slots below the first leaf's offset (overhang of the previous tile's last leaf) stay padding.
+        // One block-wide scan, four consecutive leaves per thread. Leaves of more than kTileCap / 2 particles (many
+        // coincident particles) take the serial greedy packing instead.
+        static_assert(kMaxLeaves == 4 * kSearchThreads, "numbering scan: four leaves per thread");
+        const int cMax = (s.maxLeafCount + 3) & ~3;
+        if (2 * cMax <= kTileCap)
         {
-            const int node = leafTmp[q];
-            double    cx = a.tree.centers[3 * node] - ox, cy = a.tree.centers[3 * node + 1] - oy,
-                   cz = a.tree.centers[3 * node + 2] - oz;
-            if (!foldMode)
+            const int B = kTileCap - cMax;
+            int       c[4], nw[4], sc = 0, sw = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
             {
-                cx -= box.plx * rint(cx * box.ilx);
-                cy -= box.ply * rint(cy * box.ily);
-                cz -= box.plz * rint(cz * box.ilz);
+                const int q = 4 * t + k;
+                const int n = q < L ? s.leafKey[q] : 0;
+                c[k]        = (n + 3) & ~3;
+                nw[k]       = (n + 31) >> 5;
+                sc += c[k], sw += nw[k];
             }
-            const float slop    = E * 2e-6f;
-            s.leafBox[q * 6]     = float(cx);
-            s.leafBox[q * 6 + 1] = float(cy);
-            s.leafBox[q * 6 + 2] = float(cz);
-            s.leafBox[q * 6 + 3] = __double2float_ru(a.tree.sizes[3 * node]) * 1.00001f + slop;
-            s.leafBox[q * 6 + 4] = __double2float_ru(a.tree.sizes[3 * node + 1]) * 1.00001f + slop;
-            s.leafBox[q * 6 + 5] = __double2float_ru(a.tree.sizes[3 * node + 2]) * 1.00001f + slop;
+            int ic = sc, iw = sw;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int vc = __shfl_up_sync(kFullMask, ic, o), vw = __shfl_up_sync(kFullMask, iw, o);
+                if (lane >= o) ic += vc, iw += vw;
+            }
+            int* scanW = reinterpret_cast<int*>(s.red); // [2][kSearchWarps]: the bounding-box reduction is done
+            if (lane == 31) s.scan[warp] = ic, scanW[warp] = iw;
+            __syncthreads();
+            int P = ic - sc, W = iw - sw, totW = 0;
+            for (int w = 0; w < kSearchWarps; ++w)
+            {
+                if (w < warp) P += s.scan[w], W += scanW[w];
+                totW += scanW[w];
+            }
+            int prevTile = (4 * t > 0 && 4 * t <= L) ? (P - ((s.leafKey[4 * t - 1] + 3) & ~3)) / B : -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const int q = 4 * t + k;
+                if (q < L)
+                {
+                    const int tile = P / B;
+                    if (tile < kMaxTiles)
+                    {
+                        if (tile != prevTile) s.tileFirstLeaf[tile] = q;
+                        if (q == L - 1) s.tileFirstLeaf[tile + 1] = L, s.nTiles = tile + 1;
+                    }
+                    else { s.err = 1; }
+                    prevTile      = tile;
+                    s.leafTile[q] = (unsigned short)(P - tile * B);
+                    s.leafW0[q]   = (unsigned short)W;
+                    if (W + nw[k] <= kMaxWords)
+                    {
+                        for (int m = 0; m < nw[k]; ++m)
+                            s.wordLeaf[W + m] = (unsigned short)q;
+                    }
+                    else { s.err = 1; }
+                }
+                P += c[k], W += nw[k];
+            }
+            if (t == 0)
+            {
+                s.wEnd = totW;
+                if (L == 0) s.tileFirstLeaf[0] = s.tileFirstLeaf[1] = 0, s.nTiles = 1;
+            }
         }
-        __syncthreads(); // leafTmp (aliased onto usedBits) is dead from here on
-
-        // provisional numbering (every leaf starts a new 32-slot word), tiles; meanwhile everybody clears the used mask
-        if (t == 0)
+        else if (t == 0)
         {
             int W = 0, nT = 0, tileCount = 0, err = 0;
             s.tileFirstLeaf[0] = 0;
@@ -446,6 +503,13 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         const float2   nlo2      = make_float2(-r2lo, -r2lo);
         const unsigned widthBits = __float_as_uint((r2hi - r2lo) * 1.0001f);
 
+        // per-warp cull volume: bounding box of the warp's targets and its largest (inflated) search radius. A staged quad
+        // whose box is further than that from the target box cannot hold a hit or an ambiguous pair of any lane: the
+        // gaps are lower bounds of the fp32 coordinate differences the filter evaluates, 1e-5 covers the rounding.
+        const float wlx = warpMinF(tx), wly = warpMinF(ty), wlz = warpMinF(tz);
+        const float whx = warpMaxF(tx), why = warpMaxF(ty), whz = warpMaxF(tz);
+        const float wr2 = warpMaxF(r2hi) * 1.00001f;
+
         unsigned ent   = 0;
         int      selfW = -1;          // provisional word and bit of the target's own particle, once it has been staged
         unsigned selfClear = ~0u;
@@ -456,22 +520,52 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             if (lb == le) continue;
             const int tileN = s.leafTile[le - 1] + ((s.leafKey[le - 1] + 3) & ~3);
 
-            // stage
+            // stage the particles and the boxes of their quads (a quad = four lanes; padding does not count)
             {
                 int l = lb;
-                for (int p = t; p < tileN; p += T)
+                for (int p0 = 0; p0 < tileN; p0 += T)
                 {
-                    while (p >= s.leafTile[l] + ((s.leafKey[l] + 3) & ~3))
-                        ++l;
-                    const int off = p - s.leafTile[l];
-                    float4    rp  = make_float4(1e18f, 1e18f, 1e18f, 0.0f); // padding: never a hit
-                    if (off < s.leafKey[l])
+                    const int  p  = p0 + t;
+                    const bool in = p < tileN; // uniform per quad: tileN is a multiple of four
+                    float4     rp = make_float4(1e18f, 1e18f, 1e18f, 0.0f); // padding: never a hit
+                    bool       real = false;
+                    unsigned   meta = 0;
+                    if (in)
                     {
-                        const unsigned j = unsigned(s.leafFirst[l] + off);
-                        rp               = relativePosition(a, j, ox, oy, oz, foldMode);
-                        if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = 32 * int(s.leafW0[l]) + off;
+                        while (p >= s.leafTile[l] + ((s.leafKey[l] + 3) & ~3))
+                            ++l;
+                        const int off = p - s.leafTile[l]; // negative below the first leaf of the tile: padding
+                        meta = ((unsigned(s.leafW0[l]) + unsigned(max(off, 0) >> 5)) << 3) | (unsigned(off >> 2) & 7u);
+                        if (off >= 0 && off < s.leafKey[l])
+                        {
+                            const unsigned j = unsigned(s.leafFirst[l] + off);
+                            rp               = relativePosition(a, j, ox, oy, oz, foldMode);
+                            real             = true;
+                            if (j - iBlock0 < unsigned(T)) s.selfP[j - iBlock0] = 32 * int(s.leafW0[l]) + off;
+                        }
+                        s.tileX[p] = rp.x, s.tileY[p] = rp.y, s.tileZ[p] = rp.z;
                     }
-                    s.tileX[p] = rp.x, s.tileY[p] = rp.y, s.tileZ[p] = rp.z;
+                    float qlo[3] = {rp.x, rp.y, rp.z};
+                    float qhi[3] = {real ? rp.x : -1e18f, real ? rp.y : -1e18f, real ? rp.z : -1e18f};
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        qlo[d] = fminf(qlo[d], __shfl_xor_sync(kFullMask, qlo[d], 1));
+                        qhi[d] = fmaxf(qhi[d], __shfl_xor_sync(kFullMask, qhi[d], 1));
+                        qlo[d] = fminf(qlo[d], __shfl_xor_sync(kFullMask, qlo[d], 2));
+                        qhi[d] = fmaxf(qhi[d], __shfl_xor_sync(kFullMask, qhi[d], 2));
+                    }
+                    if (in && (lane & 3) == 0)
+                    {
+                        const int Q = p >> 2;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+                        {
+                            s.quadBox[d * kTileQuads + Q]       = qlo[d];
+                            s.quadBox[(3 + d) * kTileQuads + Q] = qhi[d];
+                        }
+                        s.quadMeta[Q] = (unsigned short)meta;
+                    }
                 }
             }
             __syncthreads();
@@ -481,31 +575,66 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                 selfClear    = ~(0x80000000u >> (sp & 31));
             }
 
-            for (int l = lb; l < le; ++l)
+            // which quads of the tile are within reach of this warp's targets: one quad per lane and ballot
             {
-                // does any sphere of this warp touch the leaf?
-                const float* bx  = &s.leafBox[l * 6];
-                const float  ddx = fmaxf(fabsf(bx[0] - tx) - bx[3], 0.0f);
-                const float  ddy = fmaxf(fabsf(bx[1] - ty) - bx[4], 0.0f);
-                const float  ddz = fmaxf(fabsf(bx[2] - tz) - bx[5], 0.0f);
-                const bool   touch = ddx * ddx + ddy * ddy + ddz * ddz <= r2hi;
-                if (!__any_sync(kFullMask, touch)) continue;
-
-                const int n  = s.leafKey[l];
-                const int pb = s.leafTile[l];
-                unsigned  w  = s.leafW0[l];
-                for (int c0 = 0; c0 < n; c0 += 32, ++w)
+                const int nQuad = tileN >> 2;
+#pragma unroll
+                for (int kw = 0; kw < kKeepWords; ++kw)
                 {
-                    // up to eight quads of staged particles = one provisional word; distances in packed f32x2 arithmetic
-                    const int     nq = min(8, (n - c0 + 3) >> 2);
-                    const float4* px = reinterpret_cast<const float4*>(&s.tileX[pb + c0]);
-                    const float4* py = reinterpret_cast<const float4*>(&s.tileY[pb + c0]);
-                    const float4* pz = reinterpret_cast<const float4*>(&s.tileZ[pb + c0]);
-                    unsigned      mask = 0;
-#pragma unroll 2
-                    for (int q = 0; q < nq; ++q)
+                    const int Q    = kw * 32 + lane;
+                    bool      near = false;
+                    if (Q < nQuad)
                     {
-                        const float4 X = px[q], Y = py[q], Z = pz[q];
+                        const float gx = fmaxf(fmaxf(s.quadBox[Q] - whx, wlx - s.quadBox[3 * kTileQuads + Q]), 0.0f);
+                        const float gy = fmaxf(fmaxf(s.quadBox[kTileQuads + Q] - why, wly - s.quadBox[4 * kTileQuads + Q]), 0.0f);
+                        const float gz = fmaxf(fmaxf(s.quadBox[2 * kTileQuads + Q] - whz, wlz - s.quadBox[5 * kTileQuads + Q]), 0.0f);
+                        // (a quad made of padding only has lo > hi: never in reach, also not with fold mode's r2hi)
+                        near = gx * gx + gy * gy + gz * gz <= wr2 && s.quadBox[Q] <= s.quadBox[3 * kTileQuads + Q];
+                    }
+                    const unsigned bits = __ballot_sync(kFullMask, near);
+                    if (lane == 0) s.keep[warp][kw] = bits;
+                }
+                __syncwarp();
+            }
+
+            // walk the quads in reach (set bits of the warp's keep mask); the hits of a provisional word are collected
+            // in `mask` (staged particle k of the word is bit 31 - k) and flushed when the next word begins
+            {
+                int      curW = -1;
+                unsigned mask = 0;
+                auto     flush = [&]()
+                {
+                    if (curW == selfW) mask &= selfClear; // the target itself is not a neighbour
+                    const unsigned any = __reduce_or_sync(kFullMask, mask);
+                    if (any && lane == 0) atomicOr(&s.usedBits[curW], any);
+                    if (mask)
+                    {
+                        count += __popc(mask);
+                        if (ent < kMaskRows) { maskCol[ent * 32] = make_uint2(mask, unsigned(curW)); }
+                        else { s.err = 1; }
+                        ++ent;
+                    }
+                };
+                const float4* px   = reinterpret_cast<const float4*>(s.tileX);
+                const float4* py   = reinterpret_cast<const float4*>(s.tileY);
+                const float4* pz   = reinterpret_cast<const float4*>(s.tileZ);
+                const int     nKw  = ((tileN >> 2) + 31) >> 5;
+                for (int kw = 0; kw < nKw; ++kw)
+                {
+                    unsigned bits = s.keep[warp][kw];
+                    while (bits)
+                    {
+                        const int Q = kw * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const unsigned meta = s.quadMeta[Q];
+                        const int      w = int(meta >> 3), q = int(meta & 7u);
+                        if (w != curW)
+                        {
+                            if (curW >= 0) flush();
+                            curW = w, mask = 0;
+                        }
+                        // distances of one quad in packed f32x2 arithmetic
+                        const float4 X = px[Q], Y = py[Q], Z = pz[Q];
                         const float2 dx0 = __fadd2_rn(make_float2(X.x, X.y), ntx), dx1 = __fadd2_rn(make_float2(X.z, X.w), ntx);
                         const float2 dy0 = __fadd2_rn(make_float2(Y.x, Y.y), nty), dy1 = __fadd2_rn(make_float2(Y.z, Y.w), nty);
                         const float2 dz0 = __fadd2_rn(make_float2(Z.x, Z.y), ntz), dz1 = __fadd2_rn(make_float2(Z.z, Z.w), ntz);
@@ -516,40 +645,37 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                                                 __float_as_uint(e1.y)};
                         const bool amb = (eb[0] < widthBits) | (eb[1] < widthBits) | (eb[2] < widthBits) |
                                          (eb[3] < widthBits);
+                        unsigned nib = 0;
                         if (__any_sync(kFullMask, amb))
                         {
                             // the reference's exact fp64 predicate decides inside the margin (and always in fold mode)
                             const float d2[4] = {s0.x, s0.y, s1.x, s1.y};
+                            const int   l     = s.wordLeaf[w];
+                            const int   n     = s.leafKey[l];
+                            const int   off0  = 32 * (w - int(s.leafW0[l])) + 4 * q;
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                             {
                                 bool h = eb[u] >> 31;
                                 if (!h && d2[u] < r2hi)
                                 {
-                                    const int off = c0 + 4 * q + u;
-                                    h = off < n && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), xi, yi, zi,
+                                    const int off = off0 + u;
+                                    h = unsigned(off) < unsigned(n) && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), xi, yi, zi,
                                                              usePbc, box, radiusSq);
                                 }
-                                mask = (mask << 1) | unsigned(h);
+                                nib = (nib << 1) | unsigned(h);
                             }
-                            continue;
                         }
+                        else
+                        {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            mask = __funnelshift_l(eb[u], mask, 1); // (mask << 1) | sign(e)
-                    }
-                    mask <<= 32 - 4 * nq; // staged particle c0 + k of the leaf is bit 31 - k
-                    if (int(w) == selfW) mask &= selfClear; // the target itself is not a neighbour
-                    const unsigned any = __reduce_or_sync(kFullMask, mask);
-                    if (any && lane == 0) atomicOr(&s.usedBits[w], any);
-                    if (mask)
-                    {
-                        count += __popc(mask);
-                        if (ent < kMaskRows) { maskCol[ent * 32] = make_uint2(mask, w); }
-                        else { s.err = 1; }
-                        ++ent;
+                            for (int u = 0; u < 4; ++u)
+                                nib = __funnelshift_l(eb[u], nib, 1); // (nib << 1) | sign(e)
+                        }
+                        mask |= nib << (28 - 4 * q);
                     }
                 }
+                if (curW >= 0) flush();
             }
             __syncthreads(); // all reads of the tile are done
         }
@@ -634,6 +760,9 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             const unsigned kc = min(count, ngmax);
             uint4* lp = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
             uint2  cur = make_uint2(0u, 0u), nxt = cur;
+#pragma unroll
+            for (unsigned q = 2; q < 2 + kDecodeAhead; ++q)
+                if (q < numEnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(maskCol + size_t(q) * 32));
             if (numEnt > 0) cur = maskCol[0];
             if (numEnt > 1) nxt = maskCol[32];
             unsigned r    = 2;
@@ -666,6 +795,10 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                     cur = nxt;
                     nxt = make_uint2(0u, 0u);
                     if (r < numEnt) nxt = maskCol[r * 32];
+                    // the entry just loaded is copied into `cur` on the next refill at the latest, i.e. waited for
+                    // almost at once: pull the rows further ahead into L1 (a row = the 32 lanes' entries r, 256 bytes)
+                    if (r + kDecodeAhead < numEnt)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(maskCol + size_t(r + kDecodeAhead) * 32));
                     ++r;
                     ub = s.usedBits[w], pre = s.wordPrefix[w];
                 }
@@ -738,8 +871,11 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
 }
 
 //! persistent CTAs take blocks of 128 targets from a work counter; each CTA owns one slice of the hit-mask scratch
+#ifndef SPHX_SEARCH_CTAS
+#define SPHX_SEARCH_CTAS 7 // resident CTAs per SM the register allocation aims for
+#endif
 template<bool IterateH>
-__global__ void __launch_bounds__(kSearchThreads, 6) blockSearchKernel(const __grid_constant__ SearchArgs a)
+__global__ void __launch_bounds__(kSearchThreads, SPHX_SEARCH_CTAS) blockSearchKernel(const __grid_constant__ SearchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SearchShared&   s = *reinterpret_cast<SearchShared*>(smemRaw);
