@@ -37,7 +37,7 @@ constexpr int kMaxWords      = 768;  // provisional numbering: 32 slots per word
 constexpr int kMaxTiles      = 48;
 constexpr int kFrontierCap   = 1024; // nodes per tree level that overlap the block's bounding box
 constexpr int kWordsPerThread = kMaxWords / kSearchThreads;
-constexpr unsigned kDecodeAhead = 6;  // list decode: hit-mask rows prefetched into L1 ahead of their use
+constexpr unsigned kDecodeBatch = 16; // list decode: hit-mask entries per lane staged in shared memory at a time
 constexpr int kTileQuads      = kTileCap / 4;
 constexpr int kKeepWords      = kTileQuads / 32;
 static_assert(kTileQuads % 32 == 0, "quad cull: whole ballots per tile");
@@ -48,18 +48,19 @@ struct SearchShared
     // staged particles, SoA so that four consecutive x (y, z) are one 16-byte load and pair up for the packed
     // f32x2 arithmetic; every leaf is padded to a multiple of four entries with far-away dummies
     float          tileX[kTileCap], tileY[kTileCap], tileZ[kTileCap];
-    unsigned       usedBits[kMaxWords];   // union over the block's targets of the hit masks, per provisional word
-    unsigned short wordPrefix[kMaxWords]; // number of used provisional slots before each word
-    unsigned short wordLeaf[kMaxWords];   // (sorted) leaf that owns the word
-    int            leafKey[kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
-    int            leafFirst[kMaxLeaves]; // first particle of the sorted leaf
-    unsigned short leafW0[kMaxLeaves];    // first provisional word of the leaf
-    unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
     // boxes of the staged quads (four SFC-consecutive particles of a leaf) of the current tile, relative to the block
     // origin: [lo x | lo y | lo z | hi x | hi y | hi z][kTileQuads]. Aliased by scratch of the tree walk.
     float          quadBox[6 * kTileQuads];
-    unsigned       keep[kSearchWarps][kKeepWords];     // per warp: quads of the tile within reach of its targets
-    unsigned short quadMeta[kTileQuads];               // provisional word of the quad << 3 | position in the word
+    int            leafKey[kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
+    unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
+    unsigned short quadMeta[kTileQuads];  // provisional word of the quad << 3 | position in the word
+    unsigned       keep[kSearchWarps][kKeepWords]; // per warp: quads of the tile within reach of its targets
+    // (everything above is dead once the pair tests are done: the list decode stages the hit-mask columns there)
+    unsigned       usedBits[kMaxWords];   // union over the block's targets of the hit masks, per provisional word
+    unsigned short wordPrefix[kMaxWords]; // number of used provisional slots before each word
+    unsigned short wordLeaf[kMaxWords];   // (sorted) leaf that owns the word
+    int            leafFirst[kMaxLeaves]; // first particle of the sorted leaf
+    unsigned short leafW0[kMaxLeaves];    // first provisional word of the leaf
     int            tileFirstLeaf[kMaxTiles + 1];
     double         red[6 * kSearchWarps];
     int            count[2];
@@ -754,54 +755,63 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         if (t == 0) begin = atomicAdd(&a.scal->candTop, unsigned(total)); // consumed after the list decode
         __syncthreads(); // wordPrefix complete
 
-        // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets. Every lane
-        // decodes its own mask column at its own pace (one neighbour per iteration, next entry prefetched), ascending.
+        // neighbour list: 16-bit candidate indices, 8 per vector, lane-interleaved per group of 32 targets. A lane's
+        // hit-mask column is copied from the L2 scratch into its private shared-memory column kDecodeBatch entries at
+        // a time (asynchronous copies, all in flight together); within a batch every lane decodes at its own pace,
+        // one neighbour per iteration, ascending. The eight 16-bit entries of a vector pass through a 128-bit shift
+        // register (entry k of the vector ends up at bits 16 k).
         {
-            const unsigned kc = min(count, ngmax);
-            uint4* lp = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
-            uint2  cur = make_uint2(0u, 0u), nxt = cur;
-#pragma unroll
-            for (unsigned q = 2; q < 2 + kDecodeAhead; ++q)
-                if (q < numEnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(maskCol + size_t(q) * 32));
-            if (numEnt > 0) cur = maskCol[0];
-            if (numEnt > 1) nxt = maskCol[32];
-            unsigned r    = 2;
-            unsigned mask = cur.x, w = cur.y;
-            cur           = nxt;
-            nxt           = make_uint2(0u, 0u);
-            if (r < numEnt) nxt = maskCol[r * 32];
-            ++r;
-            unsigned           ub = s.usedBits[w], pre = s.wordPrefix[w];
-            unsigned long long vlo = 0, vhi = 0;
-            unsigned           k   = 0;
-            while (k < kc && mask)
+            static_assert(offsetof(SearchShared, usedBits) >= kDecodeBatch * kSearchThreads * sizeof(uint2),
+                          "decode staging area");
+            const unsigned kc  = min(count, ngmax);
+            uint4*         lp  = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
+            uint2*         stg = reinterpret_cast<uint2*>(s.tileX) + t; // entry q of the batch at stg[q * T]
+            const unsigned stgAddr = unsigned(__cvta_generic_to_shared(stg));
+            const unsigned maxEnt  = warpMaxU(numEnt);
+            unsigned       k = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            for (unsigned r0 = 0; r0 < maxEnt; r0 += kDecodeBatch)
             {
-                const unsigned b = __clz(mask);
-                mask &= ~(0x80000000u >> b);
-                const unsigned           e  = pre + __popc(ub & ~(0xffffffffu >> b));
-                const unsigned long long ev = (unsigned long long)(e) << (16 * (k & 3));
-                if (k & 4) { vhi |= ev; }
-                else { vlo |= ev; }
-                ++k;
-                if ((k & 7) == 0 || k == kc)
+#pragma unroll
+                for (unsigned q = 0; q < kDecodeBatch; ++q)
                 {
-                    lp[size_t((k - 1) >> 3) * kGroupSize] =
-                        make_uint4(unsigned(vlo), unsigned(vlo >> 32), unsigned(vhi), unsigned(vhi >> 32));
-                    vlo = vhi = 0;
+                    if (r0 + q < numEnt)
+                    {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stgAddr + q * unsigned(T * sizeof(uint2))),
+                                     "l"(maskCol + size_t(r0 + q) * 32)
+                                     : "memory");
+                    }
                 }
-                if (mask == 0)
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                const unsigned nb   = numEnt > r0 ? min(kDecodeBatch, numEnt - r0) : 0u;
+                unsigned       q    = 0, mask = 0, ub = 0, pre = 0;
+                while (k < kc)
                 {
-                    mask = cur.x, w = cur.y;
-                    cur = nxt;
-                    nxt = make_uint2(0u, 0u);
-                    if (r < numEnt) nxt = maskCol[r * 32];
-                    // the entry just loaded is copied into `cur` on the next refill at the latest, i.e. waited for
-                    // almost at once: pull the rows further ahead into L1 (a row = the 32 lanes' entries r, 256 bytes)
-                    if (r + kDecodeAhead < numEnt)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(maskCol + size_t(r + kDecodeAhead) * 32));
-                    ++r;
-                    ub = s.usedBits[w], pre = s.wordPrefix[w];
+                    if (mask == 0)
+                    {
+                        if (q == nb) break;
+                        const uint2 en = stg[q * T];
+                        ++q;
+                        mask = en.x;
+                        ub = s.usedBits[en.y], pre = s.wordPrefix[en.y];
+                    }
+                    const unsigned b = __clz(mask);
+                    mask &= ~(0x80000000u >> b);
+                    const unsigned e = pre + __popc(ub & ~(0xffffffffu >> b));
+                    v0 = __funnelshift_r(v0, v1, 16), v1 = __funnelshift_r(v1, v2, 16), v2 = __funnelshift_r(v2, v3, 16);
+                    v3 = __funnelshift_r(v3, e, 16);
+                    ++k;
+                    if ((k & 7) == 0) lp[size_t((k - 1) >> 3) * kGroupSize] = make_uint4(v0, v1, v2, v3);
                 }
+            }
+            if (k & 7)
+            {
+                // last, partial vector: move its entries down to the low end
+                for (unsigned f = k & 7; f < 8; ++f)
+                {
+                    v0 = __funnelshift_r(v0, v1, 16), v1 = __funnelshift_r(v1, v2, 16), v2 = __funnelshift_r(v2, v3, 16);
+                    v3 >>= 16;
+                }
+                lp[size_t(k >> 3) * kGroupSize] = make_uint4(v0, v1, v2, v3);
             }
         }
 
