@@ -37,6 +37,10 @@ constexpr int kMaxWords      = 768;  // provisional numbering: 32 slots per word
 constexpr int kMaxTiles      = 48;
 constexpr int kFrontierCap   = 1024; // nodes per tree level that overlap the block's bounding box
 constexpr int kWordsPerThread = kMaxWords / kSearchThreads;
+#ifndef SPHX_LEAF_CLASSES
+#define SPHX_LEAF_CLASSES 8
+#endif
+constexpr int      kLeafClasses = SPHX_LEAF_CLASSES; // leaf interleave of the tiles (see the ranking step)
 constexpr unsigned kDecodeBatch = 16; // list decode: hit-mask entries per lane staged in shared memory at a time
 constexpr int kTileQuads      = kTileCap / 4;
 constexpr int kKeepWords      = kTileQuads / 32;
@@ -333,8 +337,14 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             int       rk  = 0;
             for (int m = 0; m < L; ++m)
                 rk += s.leafKey[m] < key;
-            leafTmp[rk]     = leafNode[q];
-            s.leafFirst[rk] = key;
+            // Interleave: the leaves with SFC rank = g (mod kLeafClasses) are stored together, class after class. A
+            // tile (a contiguous piece of this order) then samples the whole candidate region instead of one corner of
+            // it, so that every warp finds about the same share of its quads in every tile (the warps meet at a barrier
+            // per tile). Deterministic; candidates and list entries follow this order.
+            const int g  = rk % kLeafClasses;
+            const int ps = g * (L / kLeafClasses) + min(g, L % kLeafClasses) + rk / kLeafClasses;
+            leafTmp[ps]     = leafNode[q];
+            s.leafFirst[ps] = key;
         }
         __syncthreads();
         for (int q = t; q < L; q += T)
