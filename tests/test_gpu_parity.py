@@ -187,6 +187,87 @@ def test_find_neighbors_equals_all_to_all(sx, oracle, radius, n, gaussian, box, 
     np.testing.assert_array_equal(ig, ia)
 
 
+def _block_search_vs_all_to_all(sx, oracle, x, y, z, h, box, boundary, ngmax=384, bucket=64):
+    """block search of the hydro step (sphx_find_neighbors_sph, no h-iteration: ngmin = 1) vs the O(N^2) reference"""
+    import ctypes as C
+    from sphexa_b200.sim import HydroData, Params
+    n = x.size
+    t = sx.host.build_tree(x, y, z, box, boundary, bucket_size=bucket)
+    o = t.order
+    x, y, z, h = x[o], y[o], z[o], h[o]
+    p = Params(ng0=4, ngmax=ngmax)
+    hd = HydroData(n, 0, n, box, boundary, p, device="cuda:0")
+    hd.set_fields(x=x, y=y, z=z, h=h, m=np.full(n, 1.0 / n, np.float32))
+    hd.set_tree(t)
+    hd.find_neighbors_sph()
+    L, P = oracle.lib(), oracle.P
+    nb_a = np.zeros(n * ngmax, np.uint32)
+    nc_a = np.zeros(n, np.uint32)
+    obox = oracle.make_box(box, boundary)
+    L.orc_all2all_neighbors_f(P(x), P(y), P(z), P(h), C.c_uint(n), P(nb_a), P(nc_a), C.c_uint(ngmax), C.byref(obox))
+    assert nc_a.max() <= ngmax, "test set-up: more neighbours than the list holds"
+    np.testing.assert_array_equal(hd.get("h"), h)
+    np.testing.assert_array_equal(hd.get("nc"), nc_a + 1)
+    _, ia = csr_sorted_neighbors(nb_a, nc_a + 1, ngmax)
+    _, ig = csr_sorted_neighbors(hd.export_neighbors(), hd.get("nc"), ngmax)
+    np.testing.assert_array_equal(ig, ia)
+    return t, hd
+
+
+@pytest.mark.parametrize("kind", ["uniform_pbc", "clustered_open", "mixed_h_pbc", "small_buckets"])
+def test_block_search_equals_all_to_all(sx, oracle, kind):
+    """the block search on irregular particle sets (quad cull, interleaved tiles, precise walk): bit-exact sets"""
+    rng = np.random.default_rng(11)
+    n = 6000
+    if kind == "clustered_open":
+        pts = np.concatenate([rng.normal(0.3, 0.05, (n // 2, 3)), rng.normal(0.7, 0.12, (n // 2, 3))]).clip(0.0, 1.0 - 1e-9)
+        box, boundary, h = [0., 1.] * 3, [0, 0, 0], np.full(n, 0.018, np.float32)
+    elif kind == "mixed_h_pbc":
+        pts = rng.random((n, 3))
+        box, boundary = [0., 1.] * 3, [1, 0, 1]
+        h = (0.06 * (0.5 + rng.random(n))).astype(np.float32)  # radii differ by 3x between neighbours
+    else:
+        pts = rng.random((n, 3)) * np.array([1.43, 3.4, 6.33]) + np.array([-1.2, -0.2, -5.1])
+        box, boundary = [-1.2, 0.23, -0.2, 3.2, -5.1, 1.23], [1, 1, 1]
+        # 2h = 0.5 against a box length of 1.43: the blocks run in fold mode; bucket 16: many small leaves, ~15 neighbours
+        h = np.full(n, 0.25 if kind == "uniform_pbc" else 0.13, np.float32)
+    x, y, z = (np.ascontiguousarray(pts[:, d]) for d in range(3))
+    _block_search_vs_all_to_all(sx, oracle, x, y, z, h, box, boundary, bucket=16 if kind == "small_buckets" else 64)
+
+
+def test_block_search_capacity_error_is_loud(sx, oracle):
+    """an octree far too fine for the search radii (bucket 8 in an anisotropic box: 1.8 particles per leaf, > 800 leaves
+    in reach of one target block) exceeds the per-block tables: SPHX_ERR_TRAVERSAL, the analogue of the reference's
+    "traversal stack exhausted" (hydro_ve/xmass_gpu.cu:127), never a silent truncation"""
+    rng = np.random.default_rng(11)
+    pts = rng.random((6000, 3)) * np.array([1.43, 3.4, 6.33]) + np.array([-1.2, -0.2, -5.1])
+    x, y, z = (np.ascontiguousarray(pts[:, d]) for d in range(3))
+    with pytest.raises(sx.SphxError) as e:
+        _block_search_vs_all_to_all(sx, oracle, x, y, z, np.full(6000, 0.13, np.float32),
+                                    [-1.2, 0.23, -0.2, 3.2, -5.1, 1.23], [1, 1, 1], bucket=8)
+    assert e.value.code == 7
+
+
+def test_block_search_with_coincident_particles(sx, oracle):
+    """two clumps of 200 coincident particles each inside ONE cell of the deepest tree level: the leaf cannot be split
+    (400 particles > half a tile), which takes the serial tile numbering of the search; pairs at distance 0 count"""
+    rng = np.random.default_rng(3)
+    n_bg = 3000
+    pts = rng.random((2 * n_bg, 3))
+    pts = pts[np.linalg.norm(pts - 0.5, axis=1) > 0.15][:n_bg]  # the background does not see the clumps
+    n_bg = pts.shape[0]
+    c = np.array([0.5 + 1e-7, 0.5 + 1e-7, 0.5 + 1e-7])
+    clumps = np.concatenate([np.tile(c, (200, 1)), np.tile(c + 1.5e-7, (200, 1))])
+    pts = np.concatenate([pts, clumps])
+    h = np.concatenate([np.full(n_bg, 0.06, np.float32), np.full(400, 2e-8, np.float32)])
+    x, y, z = (np.ascontiguousarray(pts[:, d]) for d in range(3))
+    t, hd = _block_search_vs_all_to_all(sx, oracle, x, y, z, h, [0., 1.] * 3, [0, 0, 0])
+    counts = np.diff(np.asarray(t.layout))
+    assert counts.max() >= 400
+    nc = hd.get("nc")
+    assert (nc == 200).sum() == 400  # 199 coincident partners + self
+
+
 def test_edge_cases(sx):
     """empty range, ragged last group, ngmax truncation semantics, error codes"""
     d = load_golden("turb12_step0.npz")
