@@ -235,9 +235,9 @@ def measure_dist_loop(sx, sdist, glob, rank, world, dev, dist, reps=4) -> dict:
     out = {"ms": dict(zip(names, acc.tolist())), "loop_ms_per_step": float(acc.sum()),
            "particles_per_sec_whole_loop": ds.n_global / (float(acc.sum()) * 1e-3),
            "cell_level": ds.level, "max_assigned_per_rank": int(smax[0]), "max_local_per_rank": int(smax[1]),
-           "note": "dynamic SFC decomposition redone every step: device histogram + ncclAllReduce, host plan, slice "
-                   "migration (ncclSend/Recv), merge sort, halo exchange of x,y,z,h,m, local octree; includes the host "
-                   "plan and the D2H/H2D of the 8^level-cell histogram"}
+           "note": "dynamic SFC decomposition redone every step, all on the device: keys + radix sort, cell histogram + "
+                   "ncclAllReduce, decomposition plan (sphx_cell_plan_build_device; only a 2 KB summary reaches the host), "
+                   "slice migration (ncclSend/Recv), merge sort, halo exchange of x,y,z,h,m, local octree"}
     ds.close()
     return out
 

@@ -475,6 +475,31 @@ extern "C"
     void sphx_cell_plan_get(const SphxCellPlan*, uint64_t* cellSplits, int* peers, unsigned* sendOffsets,
                             unsigned* sendIdx, unsigned* recvBegin, unsigned* recvCount, unsigned* recvCells);
 
+    /* The same plan built on the device (csrc/domain_sync.cu), so that the global histogram never leaves the GPU and
+     * the only host traffic of a sync is this POD: one thread per cell decodes its Hilbert index, encodes its 26
+     * neighbours and flags halo / send cells; scans and compactions turn the flags into the receive ranges and the
+     * send index lists. Bit-identical to sphx_cell_plan_build_host (tests/test_gpu_sync_integrate.py). */
+#define SPHX_MAX_RANKS 64
+    typedef struct SphxCellPlanSummary
+    {
+        uint64_t cellSplits[SPHX_MAX_RANKS + 1];   /* rank r owns cells [cellSplits[r], cellSplits[r + 1]) */
+        uint64_t sendOffLocal[SPHX_MAX_RANKS + 1]; /* my SFC-sorted particles [.[r], .[r+1]) migrate to rank r */
+        uint64_t nGlobal, nAssigned, nHaloLeft, nHaloRight;
+        uint32_t recvCount[SPHX_MAX_RANKS]; /* halo particles received from rank r (one contiguous range each) */
+        uint32_t sendCount[SPHX_MAX_RANKS]; /* halo particles sent to rank r: sendIdx holds them rank after rank */
+        uint32_t numRecvCells, numSend;
+        uint32_t overflow; /* 1: sendCapacity too small, sendIdx is incomplete */
+        uint32_t pad;
+    } SphxCellPlanSummary;
+    size_t sphx_cell_plan_device_bytes(int level);
+    /* globalCounts, localCounts: device arrays of 8^level counts (all ranks / this rank's particles before the
+     * migration). sendIdx: device, sendCapacity entries. recvCells: device, 8^level entries, may be NULL (sorted halo
+     * cell ids, for inspection). out: HOST pointer; the call synchronises the stream. */
+    int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts, int level,
+                                    const int* periodic, int rank, int nranks, void* scratch, size_t scratchBytes,
+                                    unsigned* sendIdx, size_t sendCapacity, unsigned* recvCells,
+                                    SphxCellPlanSummary* out, void* stream);
+
     /* --- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ------------------------------------------------- */
 
 #define SPHX_UNIQUE_ID_BYTES 128

@@ -77,6 +77,16 @@ class SphxConserved(C.Structure):
                 ("angmom3", C.c_double * 3), ("totalNeighbors", C.c_ulong)]
 
 
+MAX_RANKS = 64
+
+
+class SphxCellPlanSummary(C.Structure):
+    _fields_ = [("cellSplits", C.c_uint64 * (MAX_RANKS + 1)), ("sendOffLocal", C.c_uint64 * (MAX_RANKS + 1)),
+                ("nGlobal", C.c_uint64), ("nAssigned", C.c_uint64), ("nHaloLeft", C.c_uint64),
+                ("nHaloRight", C.c_uint64), ("recvCount", C.c_uint32 * MAX_RANKS), ("sendCount", C.c_uint32 * MAX_RANKS),
+                ("numRecvCells", C.c_uint32), ("numSend", C.c_uint32), ("overflow", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class SphxTurbulenceSettings(C.Structure):
     """defaults = sphexa::TurbulenceConstants() (main/src/init/turbulence_init.hpp:47-72)"""
     _fields_ = [("solWeight", C.c_double), ("Lbox", C.c_double), ("stEnergyPrefac", C.c_double),
@@ -107,6 +117,7 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_wor
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
            "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
            "sphx_allreduce_device", "sphx_exchange_slices", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get",
+           "sphx_cell_plan_device_bytes", "sphx_cell_plan_build_device",
            "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
            "sphx_conserved_quantities", "sphx_turbulence_create", "sphx_turbulence_free", "sphx_turbulence_sizes",
@@ -175,6 +186,10 @@ def load():
     L.sphx_cell_plan_free.argtypes = [C.c_void_p]
     L.sphx_cell_plan_sizes.argtypes = [C.c_void_p, C.c_void_p]
     L.sphx_cell_plan_get.argtypes = [C.c_void_p] * 8
+    L.sphx_cell_plan_device_bytes.restype = C.c_size_t
+    L.sphx_cell_plan_device_bytes.argtypes = [C.c_int]
+    L.sphx_cell_plan_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_cell_histogram.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     L.sphx_reorder_fields.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_compute_timestep.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -22,6 +22,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -551,6 +552,295 @@ int sphx_reorder_fields(const unsigned* order, size_t n, int count, const void* 
     }
     reorderKernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(order, unsigned(n), g);
     SYNC_CUDA(cudaGetLastError());
+    return SPHX_OK;
+}
+
+} // extern "C"
+
+/* ------------------------------ decomposition plan on the device (multi-rank Domain::sync) ------------------------------ */
+
+namespace sphx
+{
+namespace
+{
+
+struct PlanDev
+{
+    SphxCellPlanSummary sum;
+    unsigned            sendBase; // running offset into sendIdx while the per-rank lists are laid out
+};
+
+//! rank that owns cell c: splits[r] <= c < splits[r + 1] (empty ranges are skipped)
+__device__ __forceinline__ int ownerOf(const uint64_t* __restrict__ splits, int nranks, uint64_t c)
+{
+    int r = 0;
+    while (r + 1 < nranks && c >= splits[r + 1])
+        ++r;
+    return r;
+}
+
+struct WidenCounts
+{
+    const unsigned* g;
+    __device__ uint64_t operator()(unsigned c) const { return g[c]; }
+};
+
+//! uniformBins (domaindecomp.hpp:99-110) on the cell prefix sums + the migration offsets of this rank's particles
+__global__ void planSplitsKernel(PlanDev* p, const uint64_t* __restrict__ prefixG, const unsigned* __restrict__ prefixL,
+                                 unsigned ncell, int rank, int nranks)
+{
+    __shared__ uint64_t cand[SPHX_MAX_RANKS + 1];
+    const int           r = threadIdx.x;
+    const uint64_t      N = prefixG[ncell];
+    if (r >= 1 && r < nranks)
+    {
+        // first index in prefixG[0 .. ncell] whose value is >= r N / R  (N r < 2^64: N < 2^58, r < 64)
+        const uint64_t target = (N * uint64_t(r)) / uint64_t(nranks);
+        unsigned       lo = 0, hi = ncell + 1;
+        while (lo < hi)
+        {
+            unsigned mid = lo + (hi - lo) / 2;
+            if (prefixG[mid] < target) { lo = mid + 1; }
+            else { hi = mid; }
+        }
+        cand[r] = min(uint64_t(lo), uint64_t(ncell));
+    }
+    __syncthreads();
+    if (r == 0)
+    {
+        SphxCellPlanSummary& s = p->sum;
+        s.cellSplits[0]        = 0;
+        for (int q = 1; q < nranks; ++q)
+            s.cellSplits[q] = max(cand[q], s.cellSplits[q - 1]);
+        s.cellSplits[nranks] = ncell;
+        for (int q = 0; q <= nranks; ++q)
+            s.sendOffLocal[q] = prefixL[s.cellSplits[q]];
+        s.nGlobal   = N;
+        s.nAssigned = prefixG[s.cellSplits[rank + 1]] - prefixG[s.cellSplits[rank]];
+        s.nHaloLeft = s.nHaloRight = 0;
+        for (int q = 0; q < SPHX_MAX_RANKS; ++q)
+            s.recvCount[q] = s.sendCount[q] = 0;
+        s.numRecvCells = s.numSend = s.overflow = s.pad = 0;
+        p->sendBase                              = 0;
+    }
+}
+
+/*! one thread per cell of this rank: which non-empty foreign cells touch it (-> halo cells of this rank) and which ranks
+ *  own them (-> this cell is sent to those ranks; adjacency is symmetric, so no request messages are needed) */
+__global__ void planAdjacencyKernel(const PlanDev* __restrict__ p, const unsigned* __restrict__ G, int level,
+                                    int perX, int perY, int perZ, int rank, int nranks,
+                                    unsigned char* __restrict__ recvFlag, uint64_t* __restrict__ sendMask)
+{
+    __shared__ uint8_t sDigit[kMaxHilbertStates * 8], sNext[kMaxHilbertStates * 8], sOct[kMaxHilbertStates * 8];
+    __shared__ uint64_t sSplits[SPHX_MAX_RANKS + 1];
+    for (int k = threadIdx.x; k < kMaxHilbertStates * 8; k += blockDim.x)
+        sDigit[k] = c_hDigit[k], sNext[k] = c_hNext[k], sOct[k] = c_hOctant[k];
+    for (int k = threadIdx.x; k <= nranks; k += blockDim.x)
+        sSplits[k] = p->sum.cellSplits[k];
+    __syncthreads();
+    const uint64_t cb = sSplits[rank], ce = sSplits[rank + 1];
+    const uint64_t c  = cb + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= ce || G[c] == 0) return;
+
+    int      cx = 0, cy = 0, cz = 0;
+    unsigned state = 0;
+    for (int l = level - 1; l >= 0; --l)
+    {
+        unsigned d = unsigned(c >> (3 * l)) & 7u;
+        unsigned o = sOct[state * 8 + d];
+        cx |= int((o >> 2) & 1u) << l, cy |= int((o >> 1) & 1u) << l, cz |= int(o & 1u) << l;
+        state = sNext[state * 8 + o];
+    }
+    const int side = 1 << level;
+    uint64_t  mask = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+            {
+                if (!dx && !dy && !dz) continue;
+                int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                if (nx < 0 || nx >= side) { if (!perX) continue; nx = (nx + side) % side; }
+                if (ny < 0 || ny >= side) { if (!perY) continue; ny = (ny + side) % side; }
+                if (nz < 0 || nz >= side) { if (!perZ) continue; nz = (nz + side) % side; }
+                uint64_t c2 = 0;
+                unsigned st = 0;
+                for (int l = level - 1; l >= 0; --l)
+                {
+                    unsigned o = ((unsigned(nx) >> l) & 1u) << 2 | ((unsigned(ny) >> l) & 1u) << 1 | ((unsigned(nz) >> l) & 1u);
+                    c2         = (c2 << 3) | sDigit[st * 8 + o];
+                    st         = sNext[st * 8 + o];
+                }
+                if (c2 >= cb && c2 < ce) continue;
+                if (G[c2] == 0) continue;
+                recvFlag[c2] = 1; // several threads may store the same value
+                mask |= uint64_t(1) << ownerOf(sSplits, nranks, c2);
+            }
+    sendMask[c] = mask;
+}
+
+__global__ void planRecvCountKernel(PlanDev* p, const unsigned* __restrict__ G, const unsigned char* __restrict__ recvFlag,
+                                    unsigned ncell, int nranks)
+{
+    unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell || !recvFlag[c]) return;
+    atomicAdd(&p->sum.recvCount[ownerOf(p->sum.cellSplits, nranks, c)], G[c]);
+    atomicAdd(&p->sum.numRecvCells, 1u);
+}
+
+__global__ void planHaloSizesKernel(PlanDev* p, int rank, int nranks)
+{
+    uint64_t left = 0, right = 0;
+    for (int r = 0; r < nranks; ++r)
+        (r < rank ? left : right) += p->sum.recvCount[r];
+    p->sum.nHaloLeft = left, p->sum.nHaloRight = right;
+}
+
+//! particles of cell c that go to rank r (0 if the cell is not sent there)
+struct SendCountOf
+{
+    const unsigned* G;
+    const uint64_t* sendMask;
+    int             r;
+    __device__ unsigned operator()(unsigned c) const { return ((sendMask[c] >> r) & 1u) ? G[c] : 0u; }
+};
+
+//! local indices (layout [halos | assigned | halos]) of the particles of the cells sent to rank r, in SFC order
+__global__ void planFillSendKernel(PlanDev* p, const unsigned* __restrict__ G, const uint64_t* __restrict__ sendMask,
+                                   const uint64_t* __restrict__ prefixG, const unsigned* __restrict__ offs, int r,
+                                   int rank, unsigned ncell, unsigned* __restrict__ sendIdx, size_t capacity)
+{
+    unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell || !((sendMask[c] >> r) & 1u)) return;
+    const uint64_t cb    = p->sum.cellSplits[rank];
+    const unsigned first = unsigned(p->sum.nHaloLeft + (prefixG[c] - prefixG[cb]));
+    const size_t   base  = size_t(p->sendBase) + offs[c];
+    const unsigned n     = G[c];
+    if (base + n > capacity)
+    {
+        p->sum.overflow = 1;
+        return;
+    }
+    for (unsigned k = 0; k < n; ++k)
+        sendIdx[base + k] = first + k;
+}
+
+__global__ void planAdvanceKernel(PlanDev* p, const unsigned* __restrict__ G, const uint64_t* __restrict__ sendMask,
+                                  const unsigned* __restrict__ offs, int r, unsigned ncell)
+{
+    unsigned last = ncell - 1;
+    unsigned tot  = offs[last] + (((sendMask[last] >> r) & 1u) ? G[last] : 0u);
+    p->sum.sendCount[r] = tot;
+    p->sendBase += tot;
+    p->sum.numSend = p->sendBase;
+}
+
+struct PlanScratch
+{
+    size_t prefixG, prefixL, recvFlag, sendMask, offs, numSel, dev, cubTemp, cubBytes, total;
+    explicit PlanScratch(int level)
+    {
+        size_t ncell = size_t(1) << (3 * level);
+        auto   al    = [](size_t v) { return (v + 255) / 256 * 256; };
+        size_t off   = 0;
+        prefixG = off, off = al(off + (ncell + 1) * sizeof(uint64_t));
+        prefixL = off, off = al(off + (ncell + 1) * sizeof(unsigned));
+        recvFlag = off, off = al(off + ncell);
+        sendMask = off, off = al(off + ncell * sizeof(uint64_t));
+        offs = off, off = al(off + ncell * sizeof(unsigned));
+        numSel = off, off = al(off + 16);
+        dev = off, off = al(off + sizeof(PlanDev));
+        size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        cub::TransformInputIterator<uint64_t, WidenCounts, cub::CountingInputIterator<unsigned>> wide(
+            cub::CountingInputIterator<unsigned>(0), WidenCounts{nullptr});
+        cub::DeviceScan::InclusiveSum(nullptr, t1, wide, (uint64_t*)nullptr, int(ncell));
+        cub::DeviceScan::InclusiveSum(nullptr, t2, (const unsigned*)nullptr, (unsigned*)nullptr, int(ncell));
+        cub::TransformInputIterator<unsigned, SendCountOf, cub::CountingInputIterator<unsigned>> sc(
+            cub::CountingInputIterator<unsigned>(0), SendCountOf{nullptr, nullptr, 0});
+        cub::DeviceScan::ExclusiveSum(nullptr, t3, sc, (unsigned*)nullptr, int(ncell));
+        cub::DeviceSelect::Flagged(nullptr, t4, cub::CountingInputIterator<unsigned>(0), (const unsigned char*)nullptr,
+                                   (unsigned*)nullptr, (unsigned*)nullptr, int(ncell));
+        cubBytes = std::max(std::max(t1, t2), std::max(t3, t4));
+        cubTemp = off, off = al(off + cubBytes);
+        total = off;
+    }
+};
+
+} // namespace
+} // namespace sphx
+
+extern "C"
+{
+
+size_t sphx_cell_plan_device_bytes(int level)
+{
+    if (level < 0 || level > 10) return 0;
+    return sphx::PlanScratch(level).total;
+}
+
+int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts, int level,
+                                const int* periodic, int rank, int nranks, void* scratch, size_t scratchBytes,
+                                unsigned* sendIdx, size_t sendCapacity, unsigned* recvCells, SphxCellPlanSummary* out,
+                                void* stream)
+{
+    using namespace sphx;
+    if (int st = sphx_device_check()) return st;
+    if (!globalCounts || !localCounts || level < 0 || level > 10 || !periodic || nranks < 1 || nranks > SPHX_MAX_RANKS ||
+        rank < 0 || rank >= nranks || !scratch || !out || (sendCapacity && !sendIdx))
+        return syncFail(SPHX_ERR_INVALID, "sphx_cell_plan_build_device: bad argument");
+    PlanScratch s(level);
+    if (scratchBytes < s.total)
+        return syncFail(SPHX_ERR_WORKSPACE,
+                        "sphx_cell_plan_build_device: scratch too small, need " + std::to_string(s.total));
+    SYNC_CUDA(uploadHilbertTables());
+    auto           cs    = static_cast<cudaStream_t>(stream);
+    char*          base  = static_cast<char*>(scratch);
+    const unsigned ncell = 1u << (3 * level);
+    auto*          prefixG  = reinterpret_cast<uint64_t*>(base + s.prefixG);
+    auto*          prefixL  = reinterpret_cast<unsigned*>(base + s.prefixL);
+    auto*          recvFlag = reinterpret_cast<unsigned char*>(base + s.recvFlag);
+    auto*          sendMask = reinterpret_cast<uint64_t*>(base + s.sendMask);
+    auto*          offs     = reinterpret_cast<unsigned*>(base + s.offs);
+    auto*          numSel   = reinterpret_cast<unsigned*>(base + s.numSel);
+    auto*          dev      = reinterpret_cast<PlanDev*>(base + s.dev);
+    void*          tmp      = base + s.cubTemp;
+    size_t         tmpBytes = s.cubBytes;
+
+    SYNC_CUDA(cudaMemsetAsync(prefixG, 0, sizeof(uint64_t), cs));
+    SYNC_CUDA(cudaMemsetAsync(prefixL, 0, sizeof(unsigned), cs));
+    SYNC_CUDA(cudaMemsetAsync(recvFlag, 0, ncell, cs));
+    SYNC_CUDA(cudaMemsetAsync(sendMask, 0, size_t(ncell) * sizeof(uint64_t), cs));
+    cub::TransformInputIterator<uint64_t, WidenCounts, cub::CountingInputIterator<unsigned>> wide(
+        cub::CountingInputIterator<unsigned>(0), WidenCounts{globalCounts});
+    SYNC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpBytes, wide, prefixG + 1, int(ncell), cs));
+    tmpBytes = s.cubBytes;
+    SYNC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpBytes, localCounts, prefixL + 1, int(ncell), cs));
+    planSplitsKernel<<<1, SPHX_MAX_RANKS, 0, cs>>>(dev, prefixG, prefixL, ncell, rank, nranks);
+    // (the own range is at most ncell cells: threads beyond it return at once)
+    planAdjacencyKernel<<<(ncell + 127) / 128, 128, 0, cs>>>(dev, globalCounts, level, periodic[0], periodic[1],
+                                                              periodic[2], rank, nranks, recvFlag, sendMask);
+    planRecvCountKernel<<<(ncell + 255) / 256, 256, 0, cs>>>(dev, globalCounts, recvFlag, ncell, nranks);
+    planHaloSizesKernel<<<1, 1, 0, cs>>>(dev, rank, nranks);
+    if (recvCells)
+    {
+        tmpBytes = s.cubBytes;
+        SYNC_CUDA(cub::DeviceSelect::Flagged(tmp, tmpBytes, cub::CountingInputIterator<unsigned>(0), recvFlag, recvCells,
+                                             numSel, int(ncell), cs));
+    }
+    for (int r = 0; r < nranks; ++r)
+    {
+        if (r == rank) continue;
+        cub::TransformInputIterator<unsigned, SendCountOf, cub::CountingInputIterator<unsigned>> sc(
+            cub::CountingInputIterator<unsigned>(0), SendCountOf{globalCounts, sendMask, r});
+        tmpBytes = s.cubBytes;
+        SYNC_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, sc, offs, int(ncell), cs));
+        planFillSendKernel<<<(ncell + 255) / 256, 256, 0, cs>>>(dev, globalCounts, sendMask, prefixG, offs, r, rank,
+                                                                ncell, sendIdx, sendCapacity);
+        planAdvanceKernel<<<1, 1, 0, cs>>>(dev, globalCounts, sendMask, offs, r, ncell);
+    }
+    SYNC_CUDA(cudaGetLastError());
+    SYNC_CUDA(cudaMemcpyAsync(out, &dev->sum, sizeof(SphxCellPlanSummary), cudaMemcpyDeviceToHost, cs));
+    SYNC_CUDA(cudaStreamSynchronize(cs));
+    if (out->overflow) return syncFail(SPHX_ERR_WORKSPACE, "sphx_cell_plan_build_device: send index capacity too small");
     return SPHX_OK;
 }
 

@@ -14,6 +14,7 @@ halo sets the ranks publish to each other (gather over the host process group), 
 from __future__ import annotations
 
 import ctypes as C
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -255,6 +256,50 @@ def cell_plan(global_counts: np.ndarray, level: int, boundary, rank: int, nranks
     return out
 
 
+def cell_plan_device(global_counts, local_counts, level: int, boundary, rank: int, nranks: int, scratch=None,
+                     send_capacity: int | None = None, want_recv_cells: bool = False):
+    """sphx_cell_plan_build_device: the plan of `rank` from device histograms (torch int32 tensors of 8^level counts).
+    Returns (CellPlan with host-side peer arrays, send_idx device tensor)."""
+    import torch
+
+    L = _cabi.load()
+    dev = global_counts.device
+    ncell = 8 ** level
+    assert global_counts.numel() == ncell and local_counts.numel() == ncell
+    need = L.sphx_cell_plan_device_bytes(level)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    cap = int(send_capacity) if send_capacity is not None else 2 * int(local_counts.sum().item()) + 65536
+    send_idx = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    recv_cells = torch.empty(ncell, dtype=torch.int32, device=dev) if want_recv_cells else None
+    per = np.array([int(b == 1) for b in boundary], np.int32)
+    out = _cabi.SphxCellPlanSummary()
+    _cabi.check(L.sphx_cell_plan_build_device(global_counts.data_ptr(), local_counts.data_ptr(), level, _p(per), rank,
+                                              nranks, scratch.data_ptr(), scratch.numel(), send_idx.data_ptr(), cap,
+                                              recv_cells.data_ptr() if recv_cells is not None else None,
+                                              C.byref(out), None))
+    recv = np.array(out.recvCount[:nranks], np.int64)
+    send = np.array(out.sendCount[:nranks], np.int64)
+    peers = [r for r in range(nranks) if r != rank and (recv[r] > 0 or send[r] > 0)]
+    n_left, n_asg = int(out.nHaloLeft), int(out.nAssigned)
+    begin, pos = {}, 0
+    for r in range(nranks):
+        if r == rank:
+            pos = n_left + n_asg  # right halos follow the assigned range
+            continue
+        begin[r] = pos
+        pos += int(recv[r])
+    cp = CellPlan(level, np.array(out.cellSplits[:nranks + 1], np.uint64), np.array(peers, np.int32),
+                  np.concatenate([[0], np.cumsum(send[peers])]).astype(np.uint32), np.zeros(0, np.uint32),
+                  np.array([begin[r] for r in peers], np.uint32), np.array([recv[r] for r in peers], np.uint32),
+                  (recv_cells[:int(out.numRecvCells)].cpu().numpy().view(np.uint32) if want_recv_cells
+                   else np.zeros(0, np.uint32)),
+                  n_asg, n_left, int(out.nHaloRight), int(out.nGlobal))
+    cp.send_off_local = np.array(out.sendOffLocal[:nranks + 1], np.int64)
+    cp.num_send = int(out.numSend)
+    return cp, send_idx, scratch
+
+
 def cell_level(box_lim, h_max: float, max_level: int = 7) -> int:
     """finest level whose cell edge is >= 2 h_max in every dimension (so the 26-neighbourhood covers every search
     sphere), capped at max_level (8^7 = 2 M cells: the histogram all-reduce and the host sweep stay cheap)"""
@@ -335,6 +380,8 @@ class DistributedSimulation:
         self.cons_scratch = torch.zeros(self.L.sphx_conserved_scratch_bytes(), dtype=torch.uint8, device=self.dev)
         self.iteration = 0
         self.timings = {}
+        self._plan_scratch = None
+        self.profile = None  # set to a dict to accumulate per-stage wall times of sync() (synchronises the device)
 
     # -- helpers ------------------------------------------------------------------------------------------------------
     def _allreduce_host(self, values, op):
@@ -383,6 +430,19 @@ class DistributedSimulation:
         L, R, me = self.L, self.nranks, self.rank
         cur = self.cur
         n_old = cur["x"].numel()
+        prof = self.profile
+
+        def tick(name):
+            # stage timing (profile runs only: synchronises the device)
+            if prof is not None:
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                prof[name] = prof.get(name, 0.0) + now - self._t0
+                self._t0 = now
+
+        if prof is not None:
+            torch.cuda.synchronize()
+            self._t0 = time.perf_counter()
         # global box: open dimensions follow the particles (makeGlobalBox, box_mpi.hpp:66-109)
         if any(b != 1 for b in self.boundary):
             lo = [float(cur[k].min()) if n_old else np.inf for k in "xyz"]
@@ -394,32 +454,39 @@ class DistributedSimulation:
         h_max = float(self._allreduce_host([float(cur["h"].max()) if n_old else 0.0], 1)[0])
         level = cell_level(self.box_lim, h_max)
         ncell = 8 ** level
+        tick("box_hmax")
 
         # 1. local SFC order, cell histogram, global histogram
         rc, keys, order = self._sfc_sort(cur["x"], cur["y"], cur["z"])
         _cabi.check(rc)
+        tick("keys_sort")
         hist = torch.zeros(ncell, dtype=torch.int32, device=self.dev)
         _cabi.check(L.sphx_cell_histogram(keys.data_ptr(), n_old, level, hist.data_ptr(), None))
-        local_counts = hist.cpu().numpy().view(np.uint32).astype(np.int64)
+        local_hist = hist
         if R > 1:
+            local_hist = hist.clone()
             _cabi.check(L.sphx_allreduce_device(self.comm, hist.data_ptr(), ncell, 0, 2, None))
-        G = hist.cpu().numpy().view(np.uint32)
+        tick("histogram_allreduce")
 
-        # 2. plan: assignment, halo cells, send lists, layout
-        cp = cell_plan(G, level, self.boundary, me, R)
-        sp = cp.cell_splits.astype(np.int64)
-        csum = np.concatenate([[0], np.cumsum(local_counts)])
-        send_off = csum[sp]  # my sorted particles [send_off[r], send_off[r+1]) belong to rank r
+        # 2. plan on the device: assignment, halo cells, send lists, layout; only the summary POD comes to the host
+        cp, send_idx, self._plan_scratch = cell_plan_device(hist, local_hist, level, self.boundary, me, R,
+                                                            scratch=self._plan_scratch,
+                                                            send_capacity=2 * n_old + 65536)
+        tick("device_plan")
+        send_off = cp.send_off_local  # my sorted particles [send_off[r], send_off[r+1]) belong to rank r
         send_cnt = np.diff(send_off)
         if R > 1:
-            allc = [None] * R
-            dist.all_gather_object(allc, send_cnt, group=self.pg)
-            recv_cnt = np.array([allc[q][me] for q in range(R)], np.int64)
+            # R x R matrix of migration counts: every rank fills its row, one all-reduce completes it
+            m = torch.zeros(R * R, dtype=torch.int64, device=self.dev)
+            m[me * R:(me + 1) * R] = torch.from_numpy(send_cnt.astype(np.int64)).to(self.dev)
+            _cabi.check(L.sphx_allreduce_device(self.comm, m.data_ptr(), R * R, 1, 2, None))
+            recv_cnt = m.view(R, R)[:, me].cpu().numpy().astype(np.int64)
         else:
             recv_cnt = send_cnt.copy()
         recv_off = np.concatenate([[0], np.cumsum(recv_cnt)])
         n_new = int(recv_off[-1])
         assert n_new == cp.n_assigned, (n_new, cp.n_assigned)
+        tick("counts_allgather")
 
         # 3. migration: sort my particles, ship one slice per peer and field, merge-sort what arrived
         sorted_ = {k: torch.empty_like(cur[k]) for k in self.SYNC_FIELDS}
@@ -438,6 +505,7 @@ class DistributedSimulation:
             _cabi.check(rc)
         else:
             arrived, order2 = sorted_, None
+        tick("migrate_sort")
 
         # 4. local arrays [halos | assigned | halos]
         n_local, first, last = cp.n_local, cp.n_halo_left, cp.n_halo_left + cp.n_assigned
@@ -460,10 +528,11 @@ class DistributedSimulation:
             for k in self.SYNC_FIELDS:
                 dstv[k].copy_(arrived[k])
         self.cur = dstv  # views into the local arrays: integrate() updates them in place
+        tick("layout_reorder")
 
         # 5. halo plan on the device, halo exchange of the fields the search and the first loop read
-        self._send_idx = torch.from_numpy(cp.send_idx.view(np.int32).copy()).to(self.dev)
-        nsend = int(cp.send_offsets[-1]) if cp.send_offsets.size else 0
+        self._send_idx = send_idx
+        nsend = cp.num_send
         buf_bytes = self.MAX_EXCHANGE_ARRAYS * ((nsend * 8 + 15) // 16 * 16) + 64
         self._send_buf = torch.empty(buf_bytes, dtype=torch.uint8, device=self.dev)
         self._plan_host = cp  # keeps the host arrays alive
@@ -476,6 +545,7 @@ class DistributedSimulation:
         self.plan = pl
         if R > 1:
             self.exchange(list(self.HALO_SYNC_FIELDS))
+        tick("halo_exchange")
 
         # 6. octree over the local particles (already in SFC order)
         while True:
@@ -488,6 +558,7 @@ class DistributedSimulation:
             break
         self.local_keys = lkeys
         self.level = level
+        tick("local_tree")
 
     def exchange(self, names):
         arrs = (C.c_void_p * len(names))(*[self.hd.f[k].data_ptr() for k in names])

@@ -308,3 +308,47 @@ def test_simulation_noh_turbulence_energy_series(sx, tag):
     np.testing.assert_allclose(got[:, 6], ref[:, 6], rtol=1e-4)             # |linear momentum| (non-zero in both cases)
     assert np.array_equal(got[:3, 8], ref[:3, 8])
     np.testing.assert_allclose(got[:, 8], ref[:, 8], rtol=2e-3)
+
+
+@pytest.mark.parametrize("level,boundary,nranks", [(3, [1, 1, 1], 2), (3, [0, 0, 0], 3), (4, [1, 0, 1], 8),
+                                                   (4, [1, 1, 1], 5), (2, [1, 1, 1], 4), (5, [0, 1, 0], 7),
+                                                   (3, [1, 1, 1], 1)])
+def test_device_cell_plan_equals_host_plan(sx, level, boundary, nranks):
+    """multi-rank Domain::sync, the decomposition plan: sphx_cell_plan_build_device (scans + one thread per cell) gives
+    exactly what the host builder derives from the same global histogram (tests/test_dist_plan.py pins that one against
+    brute force): assignment, halo cells, receive ranges, send index lists, layout sizes; plus the migration offsets"""
+    import torch
+    from sphexa_b200 import dist as sdist
+    rng = np.random.default_rng(100 * level + nranks)
+    ncell = 8 ** level
+    G = rng.integers(0, 40, ncell).astype(np.uint32)
+    G[rng.random(ncell) < 0.3] = 0            # empty cells
+    if level >= 3:
+        G[ncell // 3: ncell // 3 + ncell // 6] = 0  # an empty stretch of the curve: ranks with few or no cells near it
+    Lc = (G * rng.random(ncell)).astype(np.uint32)  # this rank's share of every cell before the migration
+    dev = torch.device("cuda:0")
+    Gd = torch.from_numpy(G.view(np.int32)).to(dev)
+    Ld = torch.from_numpy(Lc.view(np.int32)).to(dev)
+    scratch = None
+    for rank in range(nranks):
+        ref = sdist.cell_plan(G, level, boundary, rank, nranks)
+        got, send_idx, scratch = sdist.cell_plan_device(Gd, Ld, level, boundary, rank, nranks, scratch=scratch,
+                                                        send_capacity=ref.send_idx.size + 8, want_recv_cells=True)
+        np.testing.assert_array_equal(got.cell_splits, ref.cell_splits)
+        assert (got.n_assigned, got.n_halo_left, got.n_halo_right, got.n_global) == \
+               (ref.n_assigned, ref.n_halo_left, ref.n_halo_right, ref.n_global)
+        np.testing.assert_array_equal(got.peers, ref.peers)
+        np.testing.assert_array_equal(got.send_offsets, ref.send_offsets)
+        np.testing.assert_array_equal(got.recv_begin, ref.recv_begin)
+        np.testing.assert_array_equal(got.recv_count, ref.recv_count)
+        np.testing.assert_array_equal(got.recv_cells, ref.recv_cells)
+        assert got.num_send == ref.send_idx.size
+        np.testing.assert_array_equal(send_idx[:got.num_send].cpu().numpy().view(np.uint32), ref.send_idx)
+        prefix_l = np.concatenate([[0], np.cumsum(Lc.astype(np.int64))])
+        np.testing.assert_array_equal(got.send_off_local, prefix_l[ref.cell_splits.astype(np.int64)])
+    # a send list that does not fit is an error, not a truncation
+    ref = sdist.cell_plan(G, level, boundary, 0, nranks)
+    if ref.send_idx.size > 4:
+        with pytest.raises(sx.SphxError) as e:
+            sdist.cell_plan_device(Gd, Ld, level, boundary, 0, nranks, scratch=scratch, send_capacity=ref.send_idx.size - 3)
+        assert e.value.code == 4
