@@ -84,11 +84,11 @@ struct SearchArgs
     const double *x, *y, *z;
     float*        h;
     unsigned*     nc;
-    unsigned      ng0, ngmax, nkbMax, numBlocks;
+    unsigned      ng0, ngmax, nkbMax, numBlocks, maskRows;
     uint4*        list;
     float4*       cand;
     unsigned      candCapacity;
-    uint2*        maskScratch; // per resident CTA: kBlockTargets columns of kMaskRows {hit mask, provisional word}
+    uint2*        maskScratch; // per resident CTA: kBlockTargets columns of maskRows {hit mask, provisional word}
     BlockDesc*    blocks;
     StepScalars*  scal;
 };
@@ -621,8 +621,9 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                     if (mask)
                     {
                         count += __popc(mask);
-                        if (ent < kMaskRows) { maskCol[ent * 32] = make_uint2(mask, unsigned(curW)); }
-                        else { s.err = 1; }
+                        // a column holds ngmax + 1 entries or more, each with at least one neighbour: what does not
+                        // fit lies beyond the ngmax neighbours the list keeps (count goes on, as in the reference)
+                        if (ent < a.maskRows) { maskCol[ent * 32] = make_uint2(mask, unsigned(curW)); }
                         ++ent;
                     }
                 };
@@ -690,7 +691,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
             }
             __syncthreads(); // all reads of the tile are done
         }
-        numEnt = ent;
+        numEnt = min(ent, a.maskRows);
         if (s.err) break;
         // count = number of hits without the target's own particle; keeps counting beyond ngmax, as the reference does
 
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(kSearchThreads, SPHX_SEARCH_CTAS) blockSearchK
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SearchShared&   s = *reinterpret_cast<SearchShared*>(smemRaw);
     uint2* const maskCol =
-        a.maskScratch + (size_t(blockIdx.x) * kSearchWarps + (threadIdx.x >> 5)) * kMaskRows * 32 + (threadIdx.x & 31);
+        a.maskScratch + (size_t(blockIdx.x) * kSearchWarps + (threadIdx.x >> 5)) * a.maskRows * 32 + (threadIdx.x & 31);
     unsigned blk = blockIdx.x; // first block static, the following ones from the work counter (fetched one block ahead)
     while (blk < a.numBlocks)
     {
@@ -992,7 +993,7 @@ cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, c
     s.box  = makeDevBox(a.box);
     s.tree = a.tree;
     s.x = a.f.x, s.y = a.f.y, s.z = a.f.z, s.h = a.f.h, s.nc = a.f.nc;
-    s.ng0 = a.p.ng0, s.ngmax = a.p.ngmax, s.nkbMax = w.nkbMax, s.numBlocks = w.numBlocks;
+    s.ng0 = a.p.ng0, s.ngmax = a.p.ngmax, s.nkbMax = w.nkbMax, s.numBlocks = w.numBlocks, s.maskRows = w.maskRows;
     s.maskScratch  = reinterpret_cast<uint2*>(base + w.maskOff);
     s.list         = reinterpret_cast<uint4*>(base + w.listOff);
     s.cand         = reinterpret_cast<float4*>(base + w.candOff);

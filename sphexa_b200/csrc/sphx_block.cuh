@@ -30,7 +30,9 @@ constexpr int      kBlockTargets   = 128; // targets per block (T)
 constexpr int      kGroupsPerBlock = kBlockTargets / int(kGroupSize);
 constexpr unsigned kCandPerTarget  = 16;  // candidate-array capacity per assigned particle (typical use: 8-10)
 constexpr unsigned kMaxNgmaxStep   = 384; // list vectors per target: (ngmax + 8) / 8 <= 49
-constexpr unsigned kMaskRows       = 128; // hit-mask entries {mask, word} per target of the block search
+//! hit-mask entries {mask, word} per target of the block search: every entry holds at least one neighbour, so ngmax + 1
+//! entries hold any list that does not overflow ngmax (multiple of 4: the columns of a CTA stay 16-byte aligned)
+__host__ __device__ inline unsigned maskRowsOf(unsigned ngmax) { return (ngmax + 4u) & ~3u; }
 constexpr unsigned kSearchMaxCtas  = 1024; // resident CTAs of the persistent block search (each owns a scratch slice)
 constexpr int      kSearchWork     = 5;   // StepScalars::work slot of the block search (0..4: the loop kernels)
 
@@ -58,13 +60,14 @@ __host__ __device__ inline size_t   alignUp(size_t v, size_t a) { return (v + a 
 struct WorkspaceLayout
 {
     size_t   scalOff, blocksOff, listOff, candOff, maskOff, total;
-    unsigned numBlocks, nkbMax;
+    unsigned numBlocks, nkbMax, maskRows;
     size_t   candCapacity;
 
     __host__ WorkspaceLayout(size_t numAssigned, unsigned ngmax)
     {
         numBlocks    = numBlocksOf(numAssigned);
         nkbMax       = nkbMaxOf(ngmax);
+        maskRows     = maskRowsOf(ngmax);
         candCapacity = numAssigned * kCandPerTarget + size_t(kBlockTargets) * ngmax;
         scalOff      = 0;
         blocksOff    = kScalarsBytes;
@@ -73,7 +76,7 @@ struct WorkspaceLayout
         maskOff      = alignUp(candOff + candCapacity * 16, 256);
         // hit-mask scratch of the block search: one slice per resident CTA, L2-resident (written and read once per block)
         size_t ctas  = numBlocks < kSearchMaxCtas ? numBlocks : kSearchMaxCtas;
-        total        = alignUp(maskOff + ctas * kBlockTargets * kMaskRows * sizeof(uint2), 256);
+        total        = alignUp(maskOff + ctas * kBlockTargets * maskRows * sizeof(uint2), 256);
     }
 };
 
