@@ -32,11 +32,28 @@ namespace sphx
 constexpr int kSearchThreads = kBlockTargets;
 constexpr int kSearchWarps   = kSearchThreads / 32;
 constexpr int kTileCap       = 768;  // staged particles per tile (incl. padding), multiple of 4
-constexpr int kMaxLeaves     = 512;  // leaves overlapping one block's bounding box
-constexpr int kMaxWords      = 768;  // provisional numbering: 32 slots per word, every leaf starts a new word
-constexpr int kMaxTiles      = 48;
-constexpr int kFrontierCap   = 1024; // nodes per tree level that overlap the block's bounding box
-constexpr int kWordsPerThread = kMaxWords / kSearchThreads;
+/*! Per-block table sizes. The standard set fits seven CTAs per SM. A block whose reach holds more leaves (cavities and
+ *  shells of an evolved blast wave: large search spheres next to finely resolved regions) is pushed on an overflow list
+ *  and redone by the same code instantiated with the big set, one CTA per SM, with scratch arrays of its own instead of
+ *  the aliased ones. */
+struct CapsStd
+{
+    static constexpr int  kMaxLeaves   = 512;  // leaves overlapping one block's bounding box
+    static constexpr int  kMaxWords    = 768;  // provisional numbering: 32 slots per word, every leaf starts a new word
+    static constexpr int  kMaxTiles    = 48;
+    static constexpr int  kFrontierCap = 1024; // nodes per tree level that overlap the block's bounding box
+    static constexpr bool kOwnScratch  = false;
+};
+struct CapsBig
+{
+    static constexpr int  kMaxLeaves   = 4096;
+    static constexpr int  kMaxWords    = 6144;
+    static constexpr int  kMaxTiles    = 250;
+    static constexpr int  kFrontierCap = 4096;
+    static constexpr bool kOwnScratch  = true;
+};
+constexpr int kOverflowCount = 6; // StepScalars::work slots: blocks on the overflow list, work counter of the big kernel
+constexpr int kBigWork       = 7;
 #ifndef SPHX_LEAF_CLASSES
 #define SPHX_LEAF_CLASSES 8
 #endif
@@ -45,8 +62,8 @@ constexpr unsigned kDecodeBatch = 16; // list decode: hit-mask entries per lane 
 constexpr int kTileQuads      = kTileCap / 4;
 constexpr int kKeepWords      = kTileQuads / 32;
 static_assert(kTileQuads % 32 == 0, "quad cull: whole ballots per tile");
-static_assert(kMaxWords % kSearchThreads == 0, "prefix sum: a fixed number of words per thread");
 
+template<class C>
 struct SearchShared
 {
     // staged particles, SoA so that four consecutive x (y, z) are one 16-byte load and pair up for the packed
@@ -55,17 +72,21 @@ struct SearchShared
     // boxes of the staged quads (four SFC-consecutive particles of a leaf) of the current tile, relative to the block
     // origin: [lo x | lo y | lo z | hi x | hi y | hi z][kTileQuads]. Aliased by scratch of the tree walk.
     float          quadBox[6 * kTileQuads];
-    int            leafKey[kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
-    unsigned short leafTile[kMaxLeaves];  // offset of the leaf's particles in its tile
+    int            leafKey[C::kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
+    unsigned short leafTile[C::kMaxLeaves];  // offset of the leaf's particles in its tile
     unsigned short quadMeta[kTileQuads];  // provisional word of the quad << 3 | position in the word
     unsigned       keep[kSearchWarps][kKeepWords]; // per warp: quads of the tile within reach of its targets
     // (everything above is dead once the pair tests are done: the list decode stages the hit-mask columns there)
-    unsigned       usedBits[kMaxWords];   // union over the block's targets of the hit masks, per provisional word
-    unsigned short wordPrefix[kMaxWords]; // number of used provisional slots before each word
-    unsigned short wordLeaf[kMaxWords];   // (sorted) leaf that owns the word
-    int            leafFirst[kMaxLeaves]; // first particle of the sorted leaf
-    unsigned short leafW0[kMaxLeaves];    // first provisional word of the leaf
-    int            tileFirstLeaf[kMaxTiles + 1];
+    unsigned       usedBits[C::kMaxWords];   // union over the block's targets of the hit masks, per provisional word
+    unsigned short wordPrefix[C::kMaxWords]; // number of used provisional slots before each word
+    unsigned short wordLeaf[C::kMaxWords];   // (sorted) leaf that owns the word
+    int            leafFirst[C::kMaxLeaves]; // first particle of the sorted leaf
+    unsigned short leafW0[C::kMaxLeaves];    // first provisional word of the leaf
+    int            tileFirstLeaf[C::kMaxTiles + 1];
+    // scratch of the tree walk when it does not fit the aliased arrays (big set)
+    int            ownFrontier[C::kOwnScratch ? 2 * C::kFrontierCap : 1];
+    int            ownLeafNode[C::kOwnScratch ? C::kMaxLeaves : 1];
+    float4         ownTgtSph[C::kOwnScratch ? kBlockTargets : 1];
     double         red[6 * kSearchWarps];
     int            count[2];
     int            nLeaf, nTiles, err, wEnd;
@@ -90,10 +111,12 @@ struct SearchArgs
     unsigned      candCapacity;
     uint2*        maskScratch; // per resident CTA: kBlockTargets columns of maskRows {hit mask, provisional word}
     BlockDesc*    blocks;
+    unsigned*     overflowList; // blocks the standard tables could not hold (count in scal->work[kOverflowCount])
     StepScalars*  scal;
 };
 
-size_t searchSharedBytes(unsigned) { return sizeof(SearchShared); }
+template<class C>
+constexpr size_t searchSharedBytes() { return sizeof(SearchShared<C>); }
 
 //! the reference's pair predicate (findneighbors.hpp:33-60,117,134), every fp64 operation rounded separately
 __device__ __noinline__ bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
@@ -136,19 +159,24 @@ __device__ __forceinline__ float4 relativePosition(const SearchArgs& a, unsigned
  * @param blk      block index
  * @param maskCol  this thread's column of the hit-mask scratch (entry r at maskCol[32 r])
  */
-template<bool IterateH>
-__device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s, const unsigned blk,
+template<bool IterateH, class C>
+__device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>& s, const unsigned blk,
                                             uint2* __restrict__ maskCol)
 {
-    // scratch of the tree walk, aliased onto arrays that are written only later:
-    int* frontier = reinterpret_cast<int*>(s.tileX);    // [2][kFrontierCap]: until the first tile is staged
-    int* leafNode = reinterpret_cast<int*>(s.quadBox);  // leaves in traversal order: until they are ranked
+    using Shared = SearchShared<C>;
+    constexpr int kMaxLeaves = C::kMaxLeaves, kMaxWords = C::kMaxWords, kMaxTiles = C::kMaxTiles,
+                  kFrontierCap = C::kFrontierCap;
+    constexpr int kWordsPerThread = kMaxWords / kSearchThreads, kLeavesPerThread = kMaxLeaves / kSearchThreads;
+    static_assert(kMaxWords % kSearchThreads == 0 && kMaxLeaves % kSearchThreads == 0, "scans: whole items per thread");
+    // scratch of the tree walk, aliased onto arrays that are written only later (standard set):
+    int* frontier = C::kOwnScratch ? s.ownFrontier : reinterpret_cast<int*>(s.tileX); // [2][kFrontierCap]: until the first tile is staged
+    int* leafNode = C::kOwnScratch ? s.ownLeafNode : reinterpret_cast<int*>(s.quadBox); // leaves in traversal order: until they are ranked
     int* leafTmp  = reinterpret_cast<int*>(s.usedBits); // node index of the ranked leaves: until the leaf boxes exist
-    static_assert(2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX), "frontier scratch");
-    static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.quadBox), "leaf scratch");
+    static_assert(C::kOwnScratch || 2 * kFrontierCap * sizeof(int) <= 3 * sizeof(s.tileX), "frontier scratch");
+    static_assert(C::kOwnScratch || kMaxLeaves * sizeof(int) <= sizeof(s.quadBox), "leaf scratch");
     static_assert(kMaxLeaves * sizeof(int) <= sizeof(s.usedBits), "ranked-leaf scratch");
-    static_assert(offsetof(SearchShared, tileY) == offsetof(SearchShared, tileX) + sizeof(s.tileX) &&
-                      offsetof(SearchShared, tileZ) == offsetof(SearchShared, tileY) + sizeof(s.tileY),
+    static_assert(offsetof(Shared, tileY) == offsetof(Shared, tileX) + sizeof(s.tileX) &&
+                      offsetof(Shared, tileZ) == offsetof(Shared, tileY) + sizeof(s.tileY),
                   "aliased arrays must be contiguous");
 
     constexpr int T    = kBlockTargets;
@@ -177,8 +205,9 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     // only if the search sphere of at least one target touches its box. This plays the role of the reference's group
     // splits (computeGroupSplits, traversal/groups_gpu.cu:106-135), which keep a group's bounding box small.
     bool    precise = false;
-    float4* tgtSph  = reinterpret_cast<float4*>(s.quadBox + kMaxLeaves); // [T], live during the walk only
-    static_assert((kMaxLeaves + 4 * kBlockTargets) * sizeof(float) <= sizeof(s.quadBox), "target sphere scratch");
+    float4* tgtSph = C::kOwnScratch ? s.ownTgtSph : reinterpret_cast<float4*>(s.quadBox + kMaxLeaves); // [T], walk only
+    static_assert(C::kOwnScratch || (kMaxLeaves + 4 * kBlockTargets) * sizeof(float) <= sizeof(s.quadBox),
+                  "target sphere scratch");
 
     for (;;)
     {
@@ -378,18 +407,17 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         // particle counts (each padded to a multiple of four), leaf q is staged in tile P[q] / B at offset P[q] % B:
         // B = kTileCap - largest padded count, so no leaf crosses the end of the tile buffer and no tile index is
         // skipped; the slots below the first leaf's offset (overhang of the previous tile's last leaf) stay padding.
-        // One block-wide scan, four consecutive leaves per thread. Leaves of more than kTileCap / 2 particles (many
+        // One block-wide scan, kLeavesPerThread consecutive leaves per thread. Leaves of more than kTileCap / 2 particles (many
         // coincident particles) take the serial greedy packing instead.
-        static_assert(kMaxLeaves == 4 * kSearchThreads, "numbering scan: four leaves per thread");
         const int cMax = (s.maxLeafCount + 3) & ~3;
         if (2 * cMax <= kTileCap)
         {
             const int B = kTileCap - cMax;
-            int       c[4], nw[4], sc = 0, sw = 0;
+            int       c[kLeavesPerThread], nw[kLeavesPerThread], sc = 0, sw = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < kLeavesPerThread; ++k)
             {
-                const int q = 4 * t + k;
+                const int q = kLeavesPerThread * t + k;
                 const int n = q < L ? s.leafKey[q] : 0;
                 c[k]        = (n + 3) & ~3;
                 nw[k]       = (n + 31) >> 5;
@@ -411,11 +439,12 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
                 if (w < warp) P += s.scan[w], W += scanW[w];
                 totW += scanW[w];
             }
-            int prevTile = (4 * t > 0 && 4 * t <= L) ? (P - ((s.leafKey[4 * t - 1] + 3) & ~3)) / B : -1;
+            const int q0 = kLeavesPerThread * t;
+            int prevTile = (q0 > 0 && q0 <= L) ? (P - ((s.leafKey[q0 - 1] + 3) & ~3)) / B : -1;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < kLeavesPerThread; ++k)
             {
-                const int q = 4 * t + k;
+                const int q = kLeavesPerThread * t + k;
                 if (q < L)
                 {
                     const int tile = P / B;
@@ -715,10 +744,17 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     BlockDesc      desc;
     desc.ox = ox, desc.oy = oy, desc.oz = oz;
     desc.flags = foldMode ? kBlockFold : 0u;
-    desc.pad   = 0;
+    // diagnostics (sim.py: block_stats): leaves in reach, tiles, precise walk, search repetitions of the h-iteration
+    desc.pad = unsigned(min(L, 4095)) | (unsigned(min(s.nTiles, 255)) << 12) | (unsigned(min(iteration, 15)) << 20) | (precise ? 0x80000000u : 0u);
 
     if (s.err)
     {
+        if (!C::kOwnScratch)
+        {
+            // the standard tables are too small for this block: the big instantiation redoes it (h is untouched)
+            if (t == 0) a.overflowList[atomicAdd(&a.scal->work[kOverflowCount], 1u)] = blk;
+            return;
+        }
         // traversal capacity exceeded: flag it, leave an empty block behind
         if (t == 0)
         {
@@ -772,7 +808,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
         // one neighbour per iteration, ascending. The eight 16-bit entries of a vector pass through a 128-bit shift
         // register (entry k of the vector ends up at bits 16 k).
         {
-            static_assert(offsetof(SearchShared, usedBits) >= kDecodeBatch * kSearchThreads * sizeof(uint2),
+            static_assert(offsetof(Shared, usedBits) >= kDecodeBatch * kSearchThreads * sizeof(uint2),
                           "decode staging area");
             const unsigned kc  = min(count, ngmax);
             uint4*         lp  = a.list + (size_t(blk) * kGroupsPerBlock + warp) * a.nkbMax * kGroupSize + lane;
@@ -891,27 +927,45 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared& s
     }
 }
 
-//! persistent CTAs take blocks of 128 targets from a work counter; each CTA owns one slice of the hit-mask scratch
+//! persistent CTAs take blocks of 128 targets from a work counter; each CTA owns one slice of the hit-mask scratch.
+//! The big instantiation takes its blocks from the overflow list the standard one left behind.
 #ifndef SPHX_SEARCH_CTAS
 #define SPHX_SEARCH_CTAS 7 // resident CTAs per SM the register allocation aims for
 #endif
-template<bool IterateH>
-__global__ void __launch_bounds__(kSearchThreads, SPHX_SEARCH_CTAS) blockSearchKernel(const __grid_constant__ SearchArgs a)
+template<bool IterateH, class C>
+__global__ void __launch_bounds__(kSearchThreads, C::kOwnScratch ? 1 : SPHX_SEARCH_CTAS)
+    blockSearchKernel(const __grid_constant__ SearchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    SearchShared&   s = *reinterpret_cast<SearchShared*>(smemRaw);
-    uint2* const maskCol =
+    SearchShared<C>& s = *reinterpret_cast<SearchShared<C>*>(smemRaw);
+    uint2* const     maskCol =
         a.maskScratch + (size_t(blockIdx.x) * kSearchWarps + (threadIdx.x >> 5)) * a.maskRows * 32 + (threadIdx.x & 31);
-    unsigned blk = blockIdx.x; // first block static, the following ones from the work counter (fetched one block ahead)
-    while (blk < a.numBlocks)
+    if constexpr (C::kOwnScratch)
     {
-        unsigned nxt = 0;
-        if (threadIdx.x == 0) nxt = gridDim.x + atomicAdd(&a.scal->work[kSearchWork], 1u);
-        searchBlock<IterateH>(a, s, blk, maskCol);
-        __syncthreads(); // the block's shared-memory state is dead
-        if (threadIdx.x == 0) s.nextBlock = nxt;
-        __syncthreads();
-        blk = s.nextBlock;
+        const unsigned n = a.scal->work[kOverflowCount];
+        for (;;)
+        {
+            __syncthreads(); // the previous block's shared-memory state is dead
+            if (threadIdx.x == 0) s.nextBlock = atomicAdd(&a.scal->work[kBigWork], 1u);
+            __syncthreads();
+            const unsigned idx = s.nextBlock;
+            if (idx >= n) break;
+            searchBlock<IterateH, C>(a, s, a.overflowList[idx], maskCol);
+        }
+    }
+    else
+    {
+        unsigned blk = blockIdx.x; // first block static, the following ones from the work counter (fetched one block ahead)
+        while (blk < a.numBlocks)
+        {
+            unsigned nxt = 0;
+            if (threadIdx.x == 0) nxt = gridDim.x + atomicAdd(&a.scal->work[kSearchWork], 1u);
+            searchBlock<IterateH, C>(a, s, blk, maskCol);
+            __syncthreads(); // the block's shared-memory state is dead
+            if (threadIdx.x == 0) s.nextBlock = nxt;
+            __syncthreads();
+            blk = s.nextBlock;
+        }
     }
 }
 
@@ -940,19 +994,17 @@ __global__ void exportBlockNeighborsKernel(unsigned numAssigned, unsigned ngmax,
 
 /* ---------------------------------------------- launchers ---------------------------------------------- */
 
-static cudaError_t configureSearch(unsigned ngmax)
+template<class C>
+static cudaError_t configureSearch()
 {
-    static size_t configured = 0;
-    size_t        bytes      = searchSharedBytes(ngmax);
-    if (bytes <= 48 * 1024) return cudaSuccess;
-    if (bytes > configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(blockSearchKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(bytes));
-        if (e != cudaSuccess) return e;
-        configured = bytes;
-    }
-    return cudaSuccess;
+    static bool      configured = false;
+    constexpr size_t bytes      = searchSharedBytes<C>();
+    static_assert(bytes <= 227 * 1024, "search kernel shared memory exceeds the 227 KB CTA limit");
+    if (bytes <= 48 * 1024 || configured) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(blockSearchKernel<true, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(bytes));
+    if (e == cudaSuccess) configured = true;
+    return e;
 }
 
 static int smCountSearch()
@@ -974,8 +1026,8 @@ static int searchCtasPerSm()
     static int n = 0;
     if (n == 0)
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blockSearchKernel<true>, kSearchThreads,
-                                                      searchSharedBytes(0));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blockSearchKernel<true, CapsStd>, kSearchThreads,
+                                                      searchSharedBytes<CapsStd>());
         if (n <= 0) n = 1;
     }
     return n;
@@ -985,7 +1037,9 @@ cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, c
 {
     unsigned n = unsigned(a.last - a.first);
     if (n == 0) return cudaSuccess;
-    cudaError_t e = configureSearch(a.p.ngmax);
+    cudaError_t e = configureSearch<CapsStd>();
+    if (e != cudaSuccess) return e;
+    e = configureSearch<CapsBig>();
     if (e != cudaSuccess) return e;
     char*      base = static_cast<char*>(a.workspace);
     SearchArgs s;
@@ -999,9 +1053,13 @@ cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, c
     s.cand         = reinterpret_cast<float4*>(base + w.candOff);
     s.candCapacity = unsigned(w.candCapacity > 0xffffffffull ? 0xffffffffull : w.candCapacity);
     s.blocks       = reinterpret_cast<BlockDesc*>(base + w.blocksOff);
+    s.overflowList = reinterpret_cast<unsigned*>(base + w.overflowOff);
     s.scal         = reinterpret_cast<StepScalars*>(base + w.scalOff);
     unsigned grid = std::min(std::min(w.numBlocks, kSearchMaxCtas), unsigned(searchCtasPerSm() * smCountSearch()));
-    blockSearchKernel<true><<<grid, kSearchThreads, searchSharedBytes(a.p.ngmax), stream>>>(s);
+    blockSearchKernel<true, CapsStd><<<grid, kSearchThreads, searchSharedBytes<CapsStd>(), stream>>>(s);
+    // blocks on the overflow list (normally none: the CTAs read a zero count and leave)
+    unsigned gridBig = std::min(std::min(w.numBlocks, kSearchMaxCtas), unsigned(smCountSearch()));
+    blockSearchKernel<true, CapsBig><<<gridBig, kSearchThreads, searchSharedBytes<CapsBig>(), stream>>>(s);
     return cudaGetLastError();
 }
 

@@ -59,7 +59,7 @@ __host__ __device__ inline size_t   alignUp(size_t v, size_t a) { return (v + a 
 //! workspace carving, shared by api.cu and the kernels' launchers
 struct WorkspaceLayout
 {
-    size_t   scalOff, blocksOff, listOff, candOff, maskOff, total;
+    size_t   scalOff, blocksOff, listOff, candOff, maskOff, overflowOff, total;
     unsigned numBlocks, nkbMax, maskRows;
     size_t   candCapacity;
 
@@ -76,7 +76,9 @@ struct WorkspaceLayout
         maskOff      = alignUp(candOff + candCapacity * 16, 256);
         // hit-mask scratch of the block search: one slice per resident CTA, L2-resident (written and read once per block)
         size_t ctas  = numBlocks < kSearchMaxCtas ? numBlocks : kSearchMaxCtas;
-        total        = alignUp(maskOff + ctas * kBlockTargets * maskRows * sizeof(uint2), 256);
+        overflowOff  = alignUp(maskOff + ctas * kBlockTargets * maskRows * sizeof(uint2), 256);
+        // blocks the standard search tables could not hold (redone by the big instantiation)
+        total        = alignUp(overflowOff + size_t(numBlocks) * sizeof(unsigned), 256);
     }
 };
 

@@ -225,7 +225,9 @@ class HydroData:
         desc = raw.view(np.dtype([("o", np.float64, 3), ("candBegin", np.uint32), ("numCand", np.uint32),
                                   ("flags", np.uint32), ("pad", np.uint32)]))
         scal = self.workspace[:64].cpu().numpy()
-        return dict(numCand=desc["numCand"].copy(), flags=desc["flags"].copy(), origin=desc["o"].copy(),
+        pad = desc["pad"]
+        return dict(numLeaves=pad & 0xfff, numTiles=(pad >> 12) & 0xff, hRepeats=(pad >> 20) & 0xf, precise=pad >> 31,
+                    numCand=desc["numCand"].copy(), flags=desc["flags"].copy(), origin=desc["o"].copy(),
                     candBegin=desc["candBegin"].copy(), candTop=int(scal[28:32].view(np.uint32)[0]),
                     errFlags=int(scal[24:28].view(np.uint32)[0]), candCapacity=int(lay[7]))
 

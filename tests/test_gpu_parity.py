@@ -235,17 +235,17 @@ def test_block_search_equals_all_to_all(sx, oracle, kind):
     _block_search_vs_all_to_all(sx, oracle, x, y, z, h, box, boundary, bucket=16 if kind == "small_buckets" else 64)
 
 
-def test_block_search_capacity_error_is_loud(sx, oracle):
+def test_block_search_overflow_blocks_use_the_big_tables(sx, oracle):
     """an octree far too fine for the search radii (bucket 8 in an anisotropic box: 1.8 particles per leaf, > 800 leaves
-    in reach of one target block) exceeds the per-block tables: SPHX_ERR_TRAVERSAL, the analogue of the reference's
-    "traversal stack exhausted" (hydro_ve/xmass_gpu.cu:127), never a silent truncation"""
+    in reach of one target block) exceeds the standard per-block tables (512 leaves): those blocks go on the overflow
+    list and are redone by the big instantiation of the search; the result is still the all-to-all one"""
     rng = np.random.default_rng(11)
     pts = rng.random((6000, 3)) * np.array([1.43, 3.4, 6.33]) + np.array([-1.2, -0.2, -5.1])
     x, y, z = (np.ascontiguousarray(pts[:, d]) for d in range(3))
-    with pytest.raises(sx.SphxError) as e:
-        _block_search_vs_all_to_all(sx, oracle, x, y, z, np.full(6000, 0.13, np.float32),
-                                    [-1.2, 0.23, -0.2, 3.2, -5.1, 1.23], [1, 1, 1], bucket=8)
-    assert e.value.code == 7
+    _, hd = _block_search_vs_all_to_all(sx, oracle, x, y, z, np.full(6000, 0.13, np.float32),
+                                        [-1.2, 0.23, -0.2, 3.2, -5.1, 1.23], [1, 1, 1], bucket=8)
+    bs = hd.block_stats()
+    assert bs["numLeaves"].max() > 512 and bs["errFlags"] == 0
 
 
 def test_block_search_with_coincident_particles(sx, oracle):

@@ -40,7 +40,9 @@ def time_case(name, hd, steps=5, warmup=2):
             "phases_ms": acc, "mean_nc": hd.result.totalNeighbors / n, "max_nc": hd.result.maxNc,
             "h_iterated": hd.result.numHIterated,
             "candidates_per_block": {"mean": float(bs["numCand"].mean()), "max": int(bs["numCand"].max())},
-            "fold_blocks": int((bs["flags"] & 1).sum())}
+            "fold_blocks": int((bs["flags"] & 1).sum()), "precise_blocks": int(bs["precise"].sum()),
+            "leaves_per_block": {"mean": float(bs["numLeaves"].mean()), "max": int(bs["numLeaves"].max())},
+            "tiles_per_block": {"mean": float(bs["numTiles"].mean()), "max": int(bs["numTiles"].max())}}
 
 
 if __name__ == "__main__":
