@@ -302,8 +302,9 @@ def our_arm(args):
         if ex is not None:
             calls.append(("halo_exchange", ex))
     num_exchanges = sum(1 for c in calls if c[0] == "halo_exchange")
-    # reset-scalars, block search, EOS, 5 x (work-counter reset + persistent loop kernel), pack kernel per exchange
-    launches_per_step = 13 + num_exchanges
+    # reset-scalars, block search (standard + overflow instantiation), EOS, 5 x (work-counter reset + persistent loop
+    # kernel), pack kernel per exchange
+    launches_per_step = 14 + num_exchanges
 
     h0 = hd.f["h"].clone()
     alpha0 = hd.f["alpha"].clone()

@@ -24,7 +24,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
-PHASE = {"blockSearchKernel": "block_search", "XMassOp": "xmass", "GradhOp": "ve_def_gradh", "IadOp": "iad_divv_curlv",
+PHASE = {"CapsStd": "block_search", "CapsBig": "block_search_overflow", "XMassOp": "xmass", "GradhOp": "ve_def_gradh", "IadOp": "iad_divv_curlv",
          "AvOp": "av_switches", "MomentumOp": "momentum_energy", "eosKernel": "eos"}
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
