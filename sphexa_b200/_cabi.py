@@ -109,7 +109,7 @@ STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ER
           5: "SPHX_ERR_H_CONVERGENCE", 6: "SPHX_ERR_NGMAX_OVERFLOW", 7: "SPHX_ERR_TRAVERSAL", 8: "SPHX_ERR_NCCL"}
 
 # every symbol include/sphx.h declares
-EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_device_check", "sphx_workspace_bytes", "sphx_workspace_layout",
+EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_debug_candidate_chunk", "sphx_device_check", "sphx_workspace_bytes", "sphx_workspace_layout",
            "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_find_neighbors_sph", "sphx_xmass", "sphx_ve_def_gradh", "sphx_eos",
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
@@ -186,6 +186,8 @@ def load():
     L.sphx_cell_plan_free.argtypes = [C.c_void_p]
     L.sphx_cell_plan_sizes.argtypes = [C.c_void_p, C.c_void_p]
     L.sphx_cell_plan_get.argtypes = [C.c_void_p] * 8
+    L.sphx_debug_candidate_chunk.restype = None
+    L.sphx_debug_candidate_chunk.argtypes = [C.c_uint]
     L.sphx_cell_plan_device_bytes.restype = C.c_size_t
     L.sphx_cell_plan_device_bytes.argtypes = [C.c_int]
     L.sphx_cell_plan_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -117,6 +117,7 @@ extern "C"
 
 const char* sphx_last_error(void) { return g_lastError.c_str(); }
 int         sphx_abi_version(void) { return SPHX_ABI_VERSION; }
+void        sphx_debug_candidate_chunk(unsigned maxRecords) { sphx::setCandidateChunkLimit(maxRecords); }
 
 int sphx_device_check(void)
 {

@@ -88,6 +88,7 @@ struct LoopArgs
     SphxFields f;
     unsigned   first, last;
     unsigned   numBlocks, nkbMax, ngmax;
+    unsigned   chunkLimit; // test hook: candidates per chunk (0xffffffff: the capacity of the loop's buffer)
     DevBox     box;
     const BlockDesc* blocks;
     const uint4*     list;

@@ -28,7 +28,6 @@ void launchExportNeighbors(unsigned numAssigned, unsigned ngmax, const unsigned*
                            bool countsIncludeSelf, unsigned* out, cudaStream_t stream);
 
 // block search of the hydro step (search.cu)
-size_t      searchSharedBytes(unsigned ngmax);
 cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t stream);
 void launchExportBlockNeighbors(const SphxStepArgs& a, const WorkspaceLayout& w, unsigned* out, cudaStream_t stream);
 
@@ -39,6 +38,7 @@ void        launchEos(const SphxStepArgs& a, cudaStream_t s);
 cudaError_t launchIadDivvCurlv(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchAvSwitches(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchMomentumEnergy(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
+void        setCandidateChunkLimit(unsigned n);
 
 // Hilbert state machine tables for the device (host_domain.cpp)
 int hilbertTablesFlat(uint8_t* digit, uint8_t* next, uint8_t* octant, int maxStates);
