@@ -1,25 +1,33 @@
 /*! @file
- * Block neighbour search of the hydro step: octree walk, candidate staging in shared memory, fp32 pair filter with an
- * exact fp64 decision for borderline pairs, coupled h-iteration, candidate compaction and the 16-bit neighbour list.
+ * Block neighbour search of the hydro step: octree walk, candidate staging in shared memory, quad cull, fp32 pair filter
+ * with an exact fp64 decision for borderline pairs, coupled h-iteration, candidate compaction and the 16-bit neighbour
+ * list.
  *
  * Replaces (reference paths relative to /root/reference):
  *   cstone::findNeighbors            domain/include/cstone/findneighbors.hpp:77-147   (the pair predicate we must match)
  *   sph::findNeighborsSph            sph/include/sph/find_neighbors.hpp:11-44        (h-iteration)
  *   cstone::traverseNeighbors        domain/include/cstone/traversal/find_neighbors.cuh:182-489 (not followed)
  *
- * One CTA owns 128 SFC-consecutive targets (one per thread).
+ * A CTA owns 128 SFC-consecutive targets at a time (one per thread, persistent CTAs, seven per SM).
  *  1. bounding box of the targets' 2h-spheres; level-synchronous walk of the octree by all 128 threads collects the
- *     leaves that overlap it; the leaves are sorted into SFC order so that everything downstream is deterministic.
- *  2. the leaves' particles ("provisional candidates") are streamed through a 1024-entry shared-memory tile as
- *     float4 {position relative to the block origin (periodic shift applied), particle index}.
- *  3. every thread tests every staged particle of the leaves that touch one of its warp's spheres: the candidate is
- *     broadcast from shared memory, the distance is evaluated in fp32. Pairs whose fp32 distance lies within a proven
+ *     leaves that overlap it; the leaves are ranked by leaf index (deterministic) and stored interleaved (ranks = g
+ *     mod 8 together), so that a tile samples the whole candidate region and the warps' work per tile is balanced.
+ *  2. provisional numbering by a block-wide scan: every leaf starts a new 32-slot word, leaf q is staged in tile
+ *     P / B at offset P % B (P: running sum of the padded particle counts).
+ *  3. the leaves' particles are streamed through a 768-entry shared-memory tile (SoA x | y | z, fp32, relative to the
+ *     block origin, periodic shift applied); four consecutive staged particles form a quad whose bounding box is
+ *     reduced with two shuffles while staging.
+ *  4. per warp, one quad per lane: quads further from the bounding box of the warp's 32 targets than its largest
+ *     search radius are dropped (ballot -> bit mask); the warp walks the remaining quads, three LDS.128 broadcasts and
+ *     packed f32x2 arithmetic give four squared distances per lane. Pairs whose fp32 distance lies within a proven
  *     error margin of the search radius are re-decided with the reference's own un-contracted fp64 predicate (same
- *     operation order, same PBC folding), so the neighbour sets are bit-exact. Hits go to a per-thread column of a
- *     shared-memory hit buffer.
- *  4. h-iteration as in the reference: if any target of the block has to change h, the block repeats the search.
- *  5. candidates used by at least one target are compacted (bit mask + popc prefix), appended to the global candidate
- *     array, and the hit columns are rewritten as 16-bit indices into that array.
+ *     operation order, same PBC folding), so the neighbour sets are bit-exact. Hits are bit masks: {mask, word} entries
+ *     in a per-thread column of an L2-resident scratch.
+ *  5. h-iteration as in the reference: if any target of the block has to change h, the block repeats the search.
+ *  6. candidates used by at least one target are compacted (bit mask + popc prefix) and appended to the global
+ *     candidate array; the mask columns are copied back to shared memory in cp.async batches and decoded into 16-bit
+ *     indices into that array, eight per uint4 of the lane-interleaved list.
+ *  Blocks that do not fit the per-block tables go on an overflow list and are redone with 8x larger tables (CapsBig).
  */
 #include "sphx_block.cuh"
 #include "sphx_kernels.h"

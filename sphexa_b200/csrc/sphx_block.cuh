@@ -5,7 +5,8 @@
  *
  *   targets      [first, last) are cut into blocks of kBlockTargets (128) SFC-consecutive particles; block b owns
  *                targets first + 128 b ... and is made of 4 groups of 32 (one warp each).
- *   candidates   per block, the exact union of the neighbours of its targets, in ascending particle order:
+ *   candidates   per block, the exact union of the neighbours of its targets, leaf after leaf in the (deterministic,
+ *                interleaved) order in which the search staged the leaves, ascending particle index inside a leaf:
  *                cand[candBegin + c] = {x_rel, y_rel, z_rel, bits(j)} where (x_rel, ...) = float(pos_j - origin_b
  *                - periodic shift) is the candidate position relative to the block origin, already shifted to the
  *                periodic image next to the block ("shift mode"), and j is the local particle index. The loops stage
@@ -13,7 +14,8 @@
  *   list         16-bit indices into the block's candidate array, 8 per 16-byte vector, lane-interleaved per group:
  *                entries 8 kb .. 8 kb + 7 of target t = 32 g + lane are the uint4 at
  *                list[(g * nkbMax + kb) * 32 + lane], so a warp reads 512 contiguous bytes per 8 neighbours.
- *                Entries of one target are ascending. 2 bytes per neighbour instead of the reference CPU's 4.
+ *                Entries of one target are ascending in the candidate index. 2 bytes per neighbour instead of the
+ *                reference CPU's 4.
  *
  * A block whose candidate region is too large compared with a periodic box length (tiny test problems) is in
  * "fold mode": candidate positions are stored unshifted and the loops apply the reference's per-pair PBC fold
