@@ -39,7 +39,10 @@ namespace sphx
 
 constexpr int kSearchThreads = kBlockTargets;
 constexpr int kSearchWarps   = kSearchThreads / 32;
-constexpr int kTileCap       = 768;  // staged particles per tile (incl. padding), multiple of 4
+#ifndef SPHX_TILE_CAP
+#define SPHX_TILE_CAP 768
+#endif
+constexpr int kTileCap       = SPHX_TILE_CAP; // staged particles per tile (incl. padding), multiple of 128
 /*! Per-block table sizes. The standard set fits seven CTAs per SM. A block whose reach holds more leaves (cavities and
  *  shells of an evolved blast wave: large search spheres next to finely resolved regions) is pushed on an overflow list
  *  and redone by the same code instantiated with the big set, one CTA per SM, with scratch arrays of its own instead of
@@ -66,7 +69,10 @@ constexpr int kBigWork       = 7;
 #define SPHX_LEAF_CLASSES 8
 #endif
 constexpr int      kLeafClasses = SPHX_LEAF_CLASSES; // leaf interleave of the tiles (see the ranking step)
-constexpr unsigned kDecodeBatch = 16; // list decode: hit-mask entries per lane staged in shared memory at a time
+#ifndef SPHX_DECODE_BATCH
+#define SPHX_DECODE_BATCH 16
+#endif
+constexpr unsigned kDecodeBatch = SPHX_DECODE_BATCH; // list decode: hit-mask entries per lane staged in shared memory at a time
 constexpr int kTileQuads      = kTileCap / 4;
 constexpr int kKeepWords      = kTileQuads / 32;
 static_assert(kTileQuads % 32 == 0, "quad cull: whole ballots per tile");
