@@ -486,19 +486,37 @@ def our_arm(args):
     design = {k: ALGO_BYTES[k] + (0 if k == "eos" else list_b * (2 if k == "iad_divv_curlv" else 1) + cand_b)
               for k in PHASES}
 
+    # the bound that binds the neighbour kernels: warp-instruction issue (4 per SM and cycle). Instructions per launch
+    # come from the committed ncu capture of the same command (profiles/traffic.json, "inst:<phase>@sedov<side>").
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = sm_count * 4 * sm_mhz * 1e6  # warp instructions / s
+    tj_all = json.loads(tfile.read_text()) if tfile.exists() else {}
+
     def per_kernel(k):
         t = phase_ms[k] * 1e-3
-        return {"ms": phase_ms[k], "GBps": ALGO_BYTES[k] * n / t / 1e9, "frac": ALGO_BYTES[k] * n / t / 1e9 / peak,
-                "design_bytes_per_particle": design[k], "design_GBps": design[k] * n / t / 1e9,
-                "design_frac": design[k] * n / t / 1e9 / peak}
+        out = {"ms": phase_ms[k], "GBps": ALGO_BYTES[k] * n / t / 1e9, "frac": ALGO_BYTES[k] * n / t / 1e9 / peak,
+               "design_bytes_per_particle": design[k], "design_GBps": design[k] * n / t / 1e9,
+               "design_frac": design[k] * n / t / 1e9 / peak}
+        inst = tj_all.get(f"inst:{TRAFFIC_KEY.get(k, k)}@sedov{side}") if world == 1 else None
+        if inst:
+            out["warp_inst_per_launch"] = inst
+            out["issue_frac"] = inst / t / issue_peak
+        return out
 
     roofline = {"bound": "hbm", "kernel": KERNEL_OF[dom], "phase": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle": ALGO_BYTES[dom],
                 "neighbor_list_bytes_per_particle": list_b, "candidate_bytes_per_particle": cand_b,
                 "note": "achieved/frac: algorithmic bytes = compulsory field traffic only (SURVEY 8d); design_*: "
-                        "compulsory + the 16-bit neighbour list and candidate records this design stores in HBM",
+                        "compulsory + the 16-bit neighbour list and candidate records this design stores in HBM; "
+                        "issue_frac: warp instructions (ncu capture under profiles/) / time / (4 per SM and cycle), the "
+                        "bound that actually binds these kernels",
+                "issue_peak_warp_inst_per_s": issue_peak,
                 "per_kernel": {k: per_kernel(k) for k in PHASES}}
+    pk = roofline["per_kernel"]
+    if all("warp_inst_per_launch" in pk[k] for k in PHASES):
+        roofline["issue_frac_step"] = sum(pk[k]["warp_inst_per_launch"] for k in PHASES) / (ms_per_step * 1e-3) / issue_peak
 
     next_rows = None
     if world == 1 and not args.no_next_rows:

@@ -45,6 +45,8 @@ def main(raw, out, traffic_tag=None):
             if key in name and "dram__bytes_read.sum" in hdr:
                 ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
                 traffic[ph] = float(r[ir]) * UNIT.get(units[ir], 1.0) + float(r[iw]) * UNIT.get(units[iw], 1.0)
+                if "smsp__inst_executed.sum" in hdr:  # warp instructions per launch (bench.py: issue-slot bound)
+                    traffic["inst:" + ph] = float(r[hdr.index("smsp__inst_executed.sum")])
     Path(out).write_text(json.dumps(res, indent=1))
     if traffic_tag:
         tf = Path(out).parent / "traffic.json"
