@@ -381,6 +381,7 @@ class DistributedSimulation:
         self.iteration = 0
         self.timings = {}
         self._plan_scratch = None
+        self.turbulence = None  # set to a sim.Turbulence for the turbulence-ve propagator
         self.profile = None  # set to a dict to accumulate per-stage wall times of sync() (synchronises the device)
 
     # -- helpers ------------------------------------------------------------------------------------------------------
@@ -567,11 +568,15 @@ class DistributedSimulation:
 
     # -- the rest of the loop ------------------------------------------------------------------------------------------
     def compute_forces(self):
+        """HydroVeProp::computeForces; with `turbulence` set (a sim.Turbulence), TurbVeProp::computeForces: every rank
+        holds the same stirring state (same seed, same time steps) and stirs its assigned particles"""
         a = self.hd.args()
         if self.nranks > 1:
             _cabi.check(self.L.sphx_hydro_step_dist(C.byref(a), self.comm, C.byref(self.plan), C.byref(self.result)))
         else:
             _cabi.check(self.L.sphx_hydro_step(C.byref(a), None, None, C.byref(self.result)))
+        if self.turbulence is not None:
+            self.turbulence.drive(self.hd, self.p.minDt)
         return self.result
 
     def compute_conserved(self):

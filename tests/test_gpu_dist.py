@@ -15,6 +15,11 @@ OUT = ["h", "nc", "xm", "kx", "gradh", "prho", "c", "c11", "c12", "c13", "c22", 
 
 def _case(name, side):
     from sphexa_b200 import cases
+    if name == "turbstir":  # turbulence box at rest: all motion comes from the stirring (turbulence-ve propagator)
+        g = cases.turbulence_global(side)
+        for k in ("vx", "vy", "vz"):
+            g["fields"][k] = np.zeros_like(g["fields"][k])
+        return g
     return cases.sedov_global(side) if name == "sedov" else cases.noh_global(side)
 
 
@@ -106,6 +111,8 @@ def _sim_worker(rank, world, port, name, side, steps, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ds = sdist.DistributedSimulation(sx.sim, _case(name, side), rank, world, f"cuda:{rank}")
+        if name == "turbstir":
+            ds.turbulence = sx.sim.Turbulence()
         rows, stats = [], []
         for _ in range(steps):
             rows.append(ds.step())
@@ -189,3 +196,36 @@ def test_multi_gpu_loop_equals_single_gpu(world, name, side, steps):
     assert (st[:, :, 2] > st[:, :, 1]).all()                          # halos are really there
     imbalance = st[:, :, 1].max(0) / st[:, :, 1].mean(0)
     assert imbalance.max() < 1.3
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_distributed_turbulence_ve_loop(world):
+    """turbulence-ve propagator (hydro step + driveTurbulence) under the dynamic decomposition: world = 1 is bitwise the
+    single-rank Simulation; on 2 ranks every rank advances the same stirring state and stirs its own particles"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import sphexa_b200 as sx
+    from sphexa_b200 import sim
+    side, steps = 20, 10
+    merged, res = _run_sim(world, "turbstir", side, steps)
+    g = _case("turbstir", side)
+    s = sim.Simulation(g["x"].size, g["box"], g["boundary"], g["params"])
+    n = g["x"].size
+    up = {k: (v if isinstance(v, np.ndarray) and v.shape == (n,) else np.full(n, v)) for k, v in g["fields"].items()}
+    s.set_fields(x=g["x"], y=g["y"], z=g["z"], **up)
+    s.sync()
+    s.f["id"].copy_(torch.arange(n, dtype=torch.int64, device=s.device))
+    s.turbulence = sim.Turbulence()
+    rows = np.array([s.step() for _ in range(steps)], np.float64)
+    got = res[0]["rows"]
+    assert rows[-1, 4] > 0  # the stirring has set the gas in motion
+    if world == 1:
+        np.testing.assert_array_equal(got[:, 1:3], rows[:, 1:3])
+        np.testing.assert_array_equal(got[:, 8], rows[:, 8])
+        np.testing.assert_allclose(got[:, 3:6], rows[:, 3:6], rtol=1e-12)
+    else:
+        np.testing.assert_allclose(got[:, 2], rows[:, 2], rtol=1e-5)
+        np.testing.assert_allclose(got[:, 3], rows[:, 3], rtol=1e-9)
+        np.testing.assert_allclose(got[1:, 4], rows[1:, 4], rtol=1e-4)
+        np.testing.assert_array_equal(got[:3, 8], rows[:3, 8])
