@@ -41,6 +41,17 @@ TRAFFIC_KEY = {"find_neighbors": "block_search"}
 PHASES = list(ALGO_BYTES)
 
 
+def finite_json(o):
+    """strict JSON has no Infinity / NaN: non-finite numbers become null (e.g. minDtRho = inf for a fluid at rest)"""
+    if isinstance(o, float):
+        return o if o == o and abs(o) != float("inf") else None
+    if isinstance(o, dict):
+        return {k: finite_json(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [finite_json(v) for v in o]
+    return o
+
+
 def measured_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
@@ -156,7 +167,7 @@ def reference_arm(args):
             "cpu_baseline": {k: r[k] for k in ("value", "cores", "kind", "sample", "cpu_model")} | {"unit": UNIT},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "phases_ms": r["phases_ms"]}
-    print(json.dumps(line))
+    print(json.dumps(finite_json(line), allow_nan=False))
 
 
 def measure_next_rows(sx, cases, side, dev, peak, reps=5) -> dict:
@@ -553,7 +564,7 @@ def our_arm(args):
                       "candidates_per_block_max": int(bs["numCand"].max()),
                       "candidates_per_particle": bs["candTop"] / n, "fold_blocks": int((bs["flags"] & 1).sum())},
             "next_rows": next_rows if world == 1 else dist_rows, "setup_s": setup_s}
-    print(json.dumps(line))
+    print(json.dumps(finite_json(line), allow_nan=False))
     if world > 1:
         dist.destroy_process_group()
 
