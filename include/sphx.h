@@ -180,7 +180,7 @@ extern "C"
     const char* sphx_last_error(void);
     int         sphx_abi_version(void);
     /* test hook: the loops stage at most maxRecords candidates of a block at a time (blocks with more are processed in
-     * candidate chunks; normally the chunk is the shared-memory buffer of the loop, 1024 - 1536 records). 0 = default. */
+     * candidate chunks; normally the chunk is the shared-memory buffer of the loop, 1024 - 1792 records). 0 = default. */
     void sphx_debug_candidate_chunk(unsigned maxRecords);
     /* 0 if a usable CUDA device is present, SPHX_ERR_NO_DEVICE otherwise */
     int sphx_device_check(void);

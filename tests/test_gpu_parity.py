@@ -160,7 +160,7 @@ def test_step_vs_compiled_reference(sx, tmp_path, case, n, steps, hs):
 @pytest.mark.parametrize("fname,chunk", [("noh14_step0.npz", 256), ("turb12_step0.npz", 320)])
 def test_candidate_chunks(sx, fname, chunk):
     """blocks whose candidate set does not fit the shared-memory buffer of a loop (evolved states reach 1500 candidates
-    against 1280 - 1536 records) are processed in candidate chunks: forced here with small chunks (test hook), the step
+    against 1280 - 1792 records) are processed in candidate chunks: forced here with small chunks (test hook), the step
     agrees with the reference and is bit-identical to the unchunked one"""
     d = load_golden(fname)
     ref, _ = run_step_by_loops(sx, d)
