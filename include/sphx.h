@@ -469,6 +469,11 @@ extern "C"
     typedef struct SphxCellPlan SphxCellPlan;
     SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts_host, int level, const int* periodic, int rank,
                                             int nranks);
+    /* the same with a per-cell reach: rings_host[c] rings of cells around cell c hold every neighbour of its particles
+     * (ceil(2 max h of the cell / cell edge)); cell c is a halo cell of every rank that owns a cell within whose reach
+     * it lies. NULL = one ring everywhere. */
+    SphxCellPlan* sphx_cell_plan_build_host_rings(const unsigned* globalCounts_host, const unsigned char* rings_host,
+                                                  int level, const int* periodic, int rank, int nranks);
     void          sphx_cell_plan_free(SphxCellPlan*);
     /* sizes: [0] numPeers [1] send indices [2] halo cells [3] nAssigned [4] nHaloLeft [5] nHaloRight [6] nGlobal
      * [7] nranks */
@@ -496,12 +501,14 @@ extern "C"
     } SphxCellPlanSummary;
     size_t sphx_cell_plan_device_bytes(int level);
     /* globalCounts, localCounts: device arrays of 8^level counts (all ranks / this rank's particles before the
-     * migration). sendIdx: device, sendCapacity entries. recvCells: device, 8^level entries, may be NULL (sorted halo
-     * cell ids, for inspection). out: HOST pointer; the call synchronises the stream. */
-    int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts, int level,
-                                    const int* periodic, int rank, int nranks, void* scratch, size_t scratchBytes,
-                                    unsigned* sendIdx, size_t sendCapacity, unsigned* recvCells,
-                                    SphxCellPlanSummary* out, void* stream);
+     * migration). rings: device array of 8^level bytes or NULL: the reach of a cell in rings of cells (Chebyshev distance),
+     * ceil(2 max h of the cell / cell edge), identical on all ranks (all-reduced); NULL = one ring everywhere. maxRing
+     * bounds rings[] (1..16). sendIdx: device, sendCapacity entries. recvCells: device, 8^level entries, may be NULL
+     * (sorted halo cell ids, for inspection). out: HOST pointer; the call synchronises the stream. */
+    int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts,
+                                    const unsigned char* rings, int maxRing, int level, const int* periodic, int rank,
+                                    int nranks, void* scratch, size_t scratchBytes, unsigned* sendIdx,
+                                    size_t sendCapacity, unsigned* recvCells, SphxCellPlanSummary* out, void* stream);
 
     /* --- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ------------------------------------------------- */
 

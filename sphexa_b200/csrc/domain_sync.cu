@@ -625,11 +625,14 @@ __global__ void planSplitsKernel(PlanDev* p, const uint64_t* __restrict__ prefix
     }
 }
 
-/*! one thread per cell of this rank: which non-empty foreign cells touch it (-> halo cells of this rank) and which ranks
- *  own them (-> this cell is sent to those ranks; adjacency is symmetric, so no request messages are needed) */
-__global__ void planAdjacencyKernel(const PlanDev* __restrict__ p, const unsigned* __restrict__ G, int level,
-                                    int perX, int perY, int perZ, int rank, int nranks,
-                                    unsigned char* __restrict__ recvFlag, uint64_t* __restrict__ sendMask)
+/*! one thread per cell of this rank: which non-empty foreign cells lie within its reach (-> halo cells of this rank) and
+ *  which foreign cells have this cell within THEIR reach (-> this cell is sent to their owners). The reach of a cell is
+ *  rings[c] rings of cells (Chebyshev distance; 1 if rings is null); everything follows from the global arrays, so no
+ *  request messages are needed. */
+__global__ void planAdjacencyKernel(const PlanDev* __restrict__ p, const unsigned* __restrict__ G,
+                                    const unsigned char* __restrict__ rings, int maxRing, int level, int perX,
+                                    int perY, int perZ, int rank, int nranks, unsigned char* __restrict__ recvFlag,
+                                    uint64_t* __restrict__ sendMask)
 {
     __shared__ uint8_t sDigit[kMaxHilbertStates * 8], sNext[kMaxHilbertStates * 8], sOct[kMaxHilbertStates * 8];
     __shared__ uint64_t sSplits[SPHX_MAX_RANKS + 1];
@@ -652,16 +655,18 @@ __global__ void planAdjacencyKernel(const PlanDev* __restrict__ p, const unsigne
         state = sNext[state * 8 + o];
     }
     const int side = 1 << level;
+    const int Rc   = rings ? max(1, int(rings[c])) : 1;
     uint64_t  mask = 0;
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx)
+    for (int dz = -maxRing; dz <= maxRing; ++dz)
+        for (int dy = -maxRing; dy <= maxRing; ++dy)
+            for (int dx = -maxRing; dx <= maxRing; ++dx)
             {
                 if (!dx && !dy && !dz) continue;
-                int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-                if (nx < 0 || nx >= side) { if (!perX) continue; nx = (nx + side) % side; }
-                if (ny < 0 || ny >= side) { if (!perY) continue; ny = (ny + side) % side; }
-                if (nz < 0 || nz >= side) { if (!perZ) continue; nz = (nz + side) % side; }
+                const int d  = max(abs(dx), max(abs(dy), abs(dz)));
+                int       nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                if (nx < 0 || nx >= side) { if (!perX) continue; nx = ((nx % side) + side) % side; }
+                if (ny < 0 || ny >= side) { if (!perY) continue; ny = ((ny % side) + side) % side; }
+                if (nz < 0 || nz >= side) { if (!perZ) continue; nz = ((nz % side) + side) % side; }
                 uint64_t c2 = 0;
                 unsigned st = 0;
                 for (int l = level - 1; l >= 0; --l)
@@ -672,8 +677,9 @@ __global__ void planAdjacencyKernel(const PlanDev* __restrict__ p, const unsigne
                 }
                 if (c2 >= cb && c2 < ce) continue;
                 if (G[c2] == 0) continue;
-                recvFlag[c2] = 1; // several threads may store the same value
-                mask |= uint64_t(1) << ownerOf(sSplits, nranks, c2);
+                if (d <= Rc) recvFlag[c2] = 1; // several threads may store the same value
+                const int R2 = rings ? max(1, int(rings[c2])) : 1;
+                if (d <= R2) mask |= uint64_t(1) << ownerOf(sSplits, nranks, c2);
             }
     sendMask[c] = mask;
 }
@@ -777,15 +783,15 @@ size_t sphx_cell_plan_device_bytes(int level)
     return sphx::PlanScratch(level).total;
 }
 
-int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts, int level,
-                                const int* periodic, int rank, int nranks, void* scratch, size_t scratchBytes,
-                                unsigned* sendIdx, size_t sendCapacity, unsigned* recvCells, SphxCellPlanSummary* out,
-                                void* stream)
+int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* localCounts, const unsigned char* rings,
+                                int maxRing, int level, const int* periodic, int rank, int nranks, void* scratch,
+                                size_t scratchBytes, unsigned* sendIdx, size_t sendCapacity, unsigned* recvCells,
+                                SphxCellPlanSummary* out, void* stream)
 {
     using namespace sphx;
     if (int st = sphx_device_check()) return st;
     if (!globalCounts || !localCounts || level < 0 || level > 10 || !periodic || nranks < 1 || nranks > SPHX_MAX_RANKS ||
-        rank < 0 || rank >= nranks || !scratch || !out || (sendCapacity && !sendIdx))
+        rank < 0 || rank >= nranks || !scratch || !out || (sendCapacity && !sendIdx) || maxRing < 1 || maxRing > 16)
         return syncFail(SPHX_ERR_INVALID, "sphx_cell_plan_build_device: bad argument");
     PlanScratch s(level);
     if (scratchBytes < s.total)
@@ -816,8 +822,9 @@ int sphx_cell_plan_build_device(const unsigned* globalCounts, const unsigned* lo
     SYNC_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpBytes, localCounts, prefixL + 1, int(ncell), cs));
     planSplitsKernel<<<1, SPHX_MAX_RANKS, 0, cs>>>(dev, prefixG, prefixL, ncell, rank, nranks);
     // (the own range is at most ncell cells: threads beyond it return at once)
-    planAdjacencyKernel<<<(ncell + 127) / 128, 128, 0, cs>>>(dev, globalCounts, level, periodic[0], periodic[1],
-                                                              periodic[2], rank, nranks, recvFlag, sendMask);
+    planAdjacencyKernel<<<(ncell + 127) / 128, 128, 0, cs>>>(dev, globalCounts, rings, rings ? maxRing : 1, level,
+                                                              periodic[0], periodic[1], periodic[2], rank, nranks,
+                                                              recvFlag, sendMask);
     planRecvCountKernel<<<(ncell + 255) / 256, 256, 0, cs>>>(dev, globalCounts, recvFlag, ncell, nranks);
     planHaloSizesKernel<<<1, 1, 0, cs>>>(dev, rank, nranks);
     if (recvCells)

@@ -504,8 +504,8 @@ struct SphxCellPlan
     size_t                nAssigned{0}, nHaloLeft{0}, nHaloRight{0}, nGlobal{0};
 };
 
-SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level, const int* periodic, int rank,
-                                        int nranks)
+SphxCellPlan* sphx_cell_plan_build_host_rings(const unsigned* globalCounts, const unsigned char* rings, int level,
+                                              const int* periodic, int rank, int nranks)
 {
     if (!globalCounts || level < 0 || level > 10 || !periodic || rank < 0 || rank >= nranks) return nullptr;
     auto*          p      = new SphxCellPlan;
@@ -536,7 +536,18 @@ SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level,
     auto ownerOf = [&](uint64_t c)
     { return int(std::upper_bound(p->cellSplits.begin() + 1, p->cellSplits.end() - 1, c) - (p->cellSplits.begin() + 1)); };
 
-    // adjacency sweep over my non-empty cells
+    // reach of a cell in rings of cells (Chebyshev distance): 1 unless the caller passes per-cell values
+    int maxRing = 1;
+    if (rings)
+    {
+        for (uint64_t c = 0; c < ncell; ++c)
+            if (globalCounts[c]) maxRing = std::max(maxRing, int(rings[c]));
+    }
+    auto ringOf = [&](uint64_t c) { return rings ? std::max(1, int(rings[c])) : 1; };
+
+    // adjacency sweep over my non-empty cells: cell c needs every non-empty foreign cell within ringOf(c) rings (halo
+    // cells); a foreign cell c2 needs c if c lies within ringOf(c2) rings of it (send cells). Both follow from the
+    // global arrays, so no rank has to ask another one.
     std::vector<std::vector<unsigned>> sendCells(nranks);
     std::vector<unsigned>              recvCells;
     tables();
@@ -544,6 +555,7 @@ SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level,
     {
         std::vector<std::vector<unsigned>> mySend(nranks);
         std::vector<unsigned>              myRecv;
+        std::vector<int>                   sentTo;
 #pragma omp for schedule(static)
         for (int64_t c = int64_t(cb); c < int64_t(ce); ++c)
         {
@@ -551,31 +563,41 @@ SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level,
             unsigned ix, iy, iz;
             hilbertDecode(uint64_t(c) << (3 * cshift), ix, iy, iz);
             int cx = int(ix >> cshift), cy = int(iy >> cshift), cz = int(iz >> cshift);
-            int lastOwner = -1; // a cell is listed once per peer: neighbours of one cell often share the owner
-            int sentTo[26], nSent = 0;
-            (void)lastOwner;
-            for (int dz = -1; dz <= 1; ++dz)
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx)
+            const int Rc = ringOf(uint64_t(c));
+            sentTo.clear();
+            auto wrap = [&](int v, int per, bool& ok)
+            {
+                if (v >= 0 && v < side) return v;
+                if (!per)
+                {
+                    ok = false;
+                    return 0;
+                }
+                return ((v % side) + side) % side;
+            };
+            for (int dz = -maxRing; dz <= maxRing; ++dz)
+                for (int dy = -maxRing; dy <= maxRing; ++dy)
+                    for (int dx = -maxRing; dx <= maxRing; ++dx)
                     {
                         if (!dx && !dy && !dz) continue;
-                        int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-                        if (nx < 0 || nx >= side) { if (!periodic[0]) continue; nx = (nx + side) % side; }
-                        if (ny < 0 || ny >= side) { if (!periodic[1]) continue; ny = (ny + side) % side; }
-                        if (nz < 0 || nz >= side) { if (!periodic[2]) continue; nz = (nz + side) % side; }
+                        const int d  = std::max(std::abs(dx), std::max(std::abs(dy), std::abs(dz)));
+                        bool      ok = true;
+                        int       nx = wrap(cx + dx, periodic[0], ok), ny = wrap(cy + dy, periodic[1], ok),
+                            nz = wrap(cz + dz, periodic[2], ok);
+                        if (!ok) continue;
                         uint64_t c2 = hilbertEncode(unsigned(nx) << cshift, unsigned(ny) << cshift,
                                                     unsigned(nz) << cshift) >> (3 * cshift);
                         if (c2 >= cb && c2 < ce) continue;
                         if (globalCounts[c2] == 0) continue;
-                        myRecv.push_back(unsigned(c2));
-                        int  o    = ownerOf(c2);
-                        bool seen = false;
-                        for (int k = 0; k < nSent; ++k)
-                            seen |= sentTo[k] == o;
-                        if (!seen)
+                        if (d <= Rc) myRecv.push_back(unsigned(c2));
+                        if (d <= ringOf(c2))
                         {
-                            sentTo[nSent++] = o;
-                            mySend[o].push_back(unsigned(c));
+                            int o = ownerOf(c2);
+                            if (std::find(sentTo.begin(), sentTo.end(), o) == sentTo.end())
+                            {
+                                sentTo.push_back(o);
+                                mySend[o].push_back(unsigned(c));
+                            }
                         }
                     }
         }
@@ -626,6 +648,12 @@ SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level,
     }
     p->recvCells.swap(recvCells);
     return p;
+}
+
+SphxCellPlan* sphx_cell_plan_build_host(const unsigned* globalCounts, int level, const int* periodic, int rank,
+                                        int nranks)
+{
+    return sphx_cell_plan_build_host_rings(globalCounts, nullptr, level, periodic, rank, nranks);
 }
 
 void sphx_cell_plan_free(SphxCellPlan* p) { delete p; }

@@ -14,6 +14,7 @@ halo sets the ranks publish to each other (gather over the host process group), 
 from __future__ import annotations
 
 import ctypes as C
+import math
 import time
 from dataclasses import dataclass
 
@@ -233,12 +234,15 @@ class CellPlan:
         return self.n_halo_left + self.n_assigned + self.n_halo_right
 
 
-def cell_plan(global_counts: np.ndarray, level: int, boundary, rank: int, nranks: int) -> CellPlan:
+def cell_plan(global_counts: np.ndarray, level: int, boundary, rank: int, nranks: int, rings=None) -> CellPlan:
+    """host builder (test oracle of the device plan). rings: per-cell reach in rings of cells (uint8), None = 1"""
     L = _cabi.load()
     g = np.ascontiguousarray(global_counts, np.uint32)
     assert g.size == 8 ** level
     per = np.array([int(b == 1) for b in boundary], np.int32)
-    h = L.sphx_cell_plan_build_host(_p(g), level, _p(per), rank, nranks)
+    rg = None if rings is None else np.ascontiguousarray(rings, np.uint8)
+    assert rg is None or rg.size == g.size
+    h = L.sphx_cell_plan_build_host_rings(_p(g), _p(rg) if rg is not None else None, level, _p(per), rank, nranks)
     if not h:
         raise ValueError("sphx_cell_plan_build_host: bad arguments")
     try:
@@ -257,7 +261,7 @@ def cell_plan(global_counts: np.ndarray, level: int, boundary, rank: int, nranks
 
 
 def cell_plan_device(global_counts, local_counts, level: int, boundary, rank: int, nranks: int, scratch=None,
-                     send_capacity: int | None = None, want_recv_cells: bool = False):
+                     send_capacity: int | None = None, want_recv_cells: bool = False, rings=None, max_ring: int = 1):
     """sphx_cell_plan_build_device: the plan of `rank` from device histograms (torch int32 tensors of 8^level counts).
     Returns (CellPlan with host-side peer arrays, send_idx device tensor)."""
     import torch
@@ -274,8 +278,11 @@ def cell_plan_device(global_counts, local_counts, level: int, boundary, rank: in
     recv_cells = torch.empty(ncell, dtype=torch.int32, device=dev) if want_recv_cells else None
     per = np.array([int(b == 1) for b in boundary], np.int32)
     out = _cabi.SphxCellPlanSummary()
-    _cabi.check(L.sphx_cell_plan_build_device(global_counts.data_ptr(), local_counts.data_ptr(), level, _p(per), rank,
-                                              nranks, scratch.data_ptr(), scratch.numel(), send_idx.data_ptr(), cap,
+    assert rings is None or (rings.numel() == ncell and rings.dtype == torch.uint8)
+    _cabi.check(L.sphx_cell_plan_build_device(global_counts.data_ptr(), local_counts.data_ptr(),
+                                              rings.data_ptr() if rings is not None else None, max_ring, level,
+                                              _p(per), rank, nranks, scratch.data_ptr(), scratch.numel(),
+                                              send_idx.data_ptr(), cap,
                                               recv_cells.data_ptr() if recv_cells is not None else None,
                                               C.byref(out), None))
     recv = np.array(out.recvCount[:nranks], np.int64)
@@ -308,6 +315,11 @@ def cell_level(box_lim, h_max: float, max_level: int = 7) -> int:
     while lvl < max_level and ext / (1 << (lvl + 1)) >= 2.0 * h_max * 1.0001:
         lvl += 1
     return lvl
+
+
+#: the plan works on cells kRingLevels levels finer than the coarsest admissible ones and gives every cell its own reach
+#: in rings of cells: thin halos where the smoothing lengths are small, wide ones only where they are large
+RING_LEVELS = 2
 
 
 def init_comm(L, rank: int, nranks: int, device, pg=None):
@@ -453,8 +465,13 @@ class DistributedSimulation:
                 if self.boundary[d] != 1:
                     self.box_lim[2 * d], self.box_lim[2 * d + 1] = float(lo[d]), float(hi[d])
         h_max = float(self._allreduce_host([float(cur["h"].max()) if n_old else 0.0], 1)[0])
-        level = cell_level(self.box_lim, h_max)
+        # cells RING_LEVELS finer than the coarsest level whose edge is >= 2 max(h); a cell reaches ceil(2 h_cell / edge)
+        # rings of cells, h_cell = largest h in the cell over all ranks
+        coarse = cell_level(self.box_lim, h_max)
+        level = min(7, coarse + RING_LEVELS)
         ncell = 8 ** level
+        edge = min(self.box_lim[2 * d + 1] - self.box_lim[2 * d] for d in range(3)) / (1 << level)
+        max_ring = max(1, min(16, int(math.ceil(2.0 * h_max * 1.0001 / edge))))
         tick("box_hmax")
 
         # 1. local SFC order, cell histogram, global histogram
@@ -467,12 +484,21 @@ class DistributedSimulation:
         if R > 1:
             local_hist = hist.clone()
             _cabi.check(L.sphx_allreduce_device(self.comm, hist.data_ptr(), ncell, 0, 2, None))
+        # largest h per cell (this rank, then all ranks) -> reach of the cell in rings
+        hcell = torch.zeros(ncell, dtype=torch.float32, device=self.dev)
+        if n_old:
+            cell_of = (keys >> (3 * (21 - level))).to(torch.int64)
+            hcell.scatter_reduce_(0, cell_of, cur["h"][order.to(torch.int64)], reduce="amax", include_self=True)
+        if R > 1:
+            _cabi.check(L.sphx_allreduce_device(self.comm, hcell.data_ptr(), ncell, 2, 1, None))
+        rings = torch.ceil(hcell.double() * (2.0 * 1.0001 / edge)).clamp_(1, max_ring).to(torch.uint8)
         tick("histogram_allreduce")
 
         # 2. plan on the device: assignment, halo cells, send lists, layout; only the summary POD comes to the host
         cp, send_idx, self._plan_scratch = cell_plan_device(hist, local_hist, level, self.boundary, me, R,
                                                             scratch=self._plan_scratch,
-                                                            send_capacity=2 * n_old + 65536)
+                                                            send_capacity=4 * n_old + 65536, rings=rings,
+                                                            max_ring=max_ring)
         tick("device_plan")
         send_off = cp.send_off_local  # my sorted particles [send_off[r], send_off[r+1]) belong to rank r
         send_cnt = np.diff(send_off)

@@ -25,16 +25,27 @@ def _setup(n, boundary, seed, clustered):
 
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 @pytest.mark.parametrize("boundary,clustered", [([1, 1, 1], False), ([0, 0, 0], True), ([1, 0, 1], True)])
-def test_cell_plan_is_complete_and_consistent(nranks, boundary, clustered):
+@pytest.mark.parametrize("variable_h", [False, True])
+def test_cell_plan_is_complete_and_consistent(nranks, boundary, clustered, variable_h):
     n = 60000
     (x, y, z), keys, box = _setup(n, boundary, 11 + nranks, clustered)
     level = 4
     edge = 1.0 / (1 << level)
-    h = np.full(n, 0.5 * edge * 0.999, np.float32)  # 2h just below the cell edge
-    assert sdist.cell_level(box, float(h.max())) == level
     cells = (keys >> np.uint64(3 * (21 - level))).astype(np.int64)
     G = np.bincount(cells, minlength=8 ** level).astype(np.uint32)
-    plans = [sdist.cell_plan(G, level, boundary, r, nranks) for r in range(nranks)]
+    if variable_h:
+        # smoothing lengths between 0.2 and 1.4 cell edges, smooth in space: cells reach 1 - 3 rings (per-cell reach =
+        # ceil(2 max h of the cell / edge), as DistributedSimulation.sync computes it)
+        h = (edge * (0.2 + 1.2 * (0.5 + 0.5 * np.sin(7.0 * x) * np.cos(5.0 * y + 3.0 * z)))).astype(np.float32)
+        hcell = np.zeros(8 ** level, np.float32)
+        np.maximum.at(hcell, cells, h)
+        rings = np.clip(np.ceil(hcell.astype(np.float64) * (2.0 * 1.0001 / edge)), 1, 3).astype(np.uint8)
+        assert rings.min() == 1 and rings.max() == 3
+    else:
+        h = np.full(n, 0.5 * edge * 0.999, np.float32)  # 2h just below the cell edge
+        assert sdist.cell_level(box, float(h.max())) == level
+        rings = None
+    plans = [sdist.cell_plan(G, level, boundary, r, nranks, rings=rings) for r in range(nranks)]
 
     # assignment: identical on all ranks, partitions the cells, balanced to within one cell
     for pl in plans:

@@ -330,10 +330,14 @@ def test_device_cell_plan_equals_host_plan(sx, level, boundary, nranks):
     Gd = torch.from_numpy(G.view(np.int32)).to(dev)
     Ld = torch.from_numpy(Lc.view(np.int32)).to(dev)
     scratch = None
+    # per-cell reach: one ring everywhere (None) or 1 - 3 rings (cells with large smoothing lengths reach further)
+    rings = None if (level + nranks) % 2 else rng.choice(np.array([1, 1, 1, 2, 3], np.uint8), ncell)
+    rings_d = None if rings is None else torch.from_numpy(rings).to(dev)
     for rank in range(nranks):
-        ref = sdist.cell_plan(G, level, boundary, rank, nranks)
+        ref = sdist.cell_plan(G, level, boundary, rank, nranks, rings=rings)
         got, send_idx, scratch = sdist.cell_plan_device(Gd, Ld, level, boundary, rank, nranks, scratch=scratch,
-                                                        send_capacity=ref.send_idx.size + 8, want_recv_cells=True)
+                                                        send_capacity=ref.send_idx.size + 8, want_recv_cells=True,
+                                                        rings=rings_d, max_ring=3)
         np.testing.assert_array_equal(got.cell_splits, ref.cell_splits)
         assert (got.n_assigned, got.n_halo_left, got.n_halo_right, got.n_global) == \
                (ref.n_assigned, ref.n_halo_left, ref.n_halo_right, ref.n_global)
@@ -347,8 +351,9 @@ def test_device_cell_plan_equals_host_plan(sx, level, boundary, nranks):
         prefix_l = np.concatenate([[0], np.cumsum(Lc.astype(np.int64))])
         np.testing.assert_array_equal(got.send_off_local, prefix_l[ref.cell_splits.astype(np.int64)])
     # a send list that does not fit is an error, not a truncation
-    ref = sdist.cell_plan(G, level, boundary, 0, nranks)
+    ref = sdist.cell_plan(G, level, boundary, 0, nranks, rings=rings)
     if ref.send_idx.size > 4:
         with pytest.raises(sx.SphxError) as e:
-            sdist.cell_plan_device(Gd, Ld, level, boundary, 0, nranks, scratch=scratch, send_capacity=ref.send_idx.size - 3)
+            sdist.cell_plan_device(Gd, Ld, level, boundary, 0, nranks, scratch=scratch, send_capacity=ref.send_idx.size - 3,
+                                   rings=rings_d, max_ring=3)
         assert e.value.code == 4

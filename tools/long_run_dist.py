@@ -34,6 +34,31 @@ for k in range(steps):
         loads.append({"step": k, "assigned_min": int(mn[0]), "assigned_max": int(mx[0]), "local_max": int(mx[1]),
                       "cell_level": ds.level})
 rows = np.array(rows, dtype=np.float64)
+
+# halo completeness on the evolved state: one more sync + search on N ranks, then the same search on one rank over the
+# gathered particle set; the search is bit-exact, so nc and h must agree particle by particle
+ds.sync()
+mine = {k: ds.assigned(k).copy() for k in ("id", "x", "y", "z", "h")}
+ds.compute_forces()
+mine["nc"], mine["h_out"] = ds.assigned("nc").copy(), ds.assigned("h").copy()
+parts = [None] * world
+if world > 1:
+    dist.all_gather_object(parts, mine)
+else:
+    parts = [mine]
+halo_check = None
+if rank == 0:
+    from sphexa_b200 import host
+    from sphexa_b200.sim import HydroData
+    g = {k: np.concatenate([p[k] for p in parts]) for k in mine}
+    t = host.build_tree(g["x"], g["y"], g["z"], ds.box_lim, ds.boundary, bucket_size=64)
+    o = t.order
+    hd = HydroData(g["x"].size, 0, g["x"].size, ds.box_lim, ds.boundary, ds.p, device=dev)
+    hd.set_fields(x=g["x"][o], y=g["y"][o], z=g["z"][o], h=g["h"][o], m=np.full(o.size, 1.0 / o.size, np.float32))
+    hd.set_tree(t)
+    hd.find_neighbors_sph()
+    halo_check = {"particles": int(o.size), "nc_mismatches": int((hd.get("nc") != g["nc"][o]).sum()),
+                  "h_mismatches": int((hd.get("h") != g["h_out"][o]).sum())}
 if rank == 0:
     make = {"sedov": cases.make_sedov_sim, "noh": cases.make_noh_sim, "turbulence": cases.make_turbulence_sim}[case]
     s = make(sx, side, device=dev)
@@ -43,5 +68,6 @@ if rank == 0:
                       "max_rel_diff_vs_single_rank": {"dt": rel(rows[:, 2], ref[:, 2]), "etot": rel(rows[:, 3], ref[:, 3]),
                                                       "ecin": rel(rows[1:, 4], ref[1:, 4]), "eint": rel(rows[:, 5], ref[:, 5])},
                       "neighbour_totals_equal_steps": int(np.sum(rows[:, 8] == ref[:, 8])),
-                      "etot_first_last": [rows[0, 3], rows[-1, 3]], "load": loads}))
+                      "etot_first_last": [rows[0, 3], rows[-1, 3]], "halo_check_on_final_state": halo_check,
+                      "load": loads}))
 ds.close()
