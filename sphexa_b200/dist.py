@@ -438,7 +438,6 @@ class DistributedSimulation:
     # -- Domain::sync -------------------------------------------------------------------------------------------------
     def sync(self):
         import torch
-        import torch.distributed as dist
 
         L, R, me = self.L, self.nranks, self.rank
         cur = self.cur

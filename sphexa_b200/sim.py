@@ -7,7 +7,7 @@ out of libsphx.so.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import torch

@@ -1,5 +1,10 @@
-import sys, json
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+"""Cost of the candidate-chunk path of the loops (test hook sphx_debug_candidate_chunk): Sedov 128^3 with every block
+staged in two chunks against the unchunked step. usage: python tools/chunk_timing.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import sphexa_b200 as sx
 from sphexa_b200 import cases
 from case_timings import time_case
