@@ -108,3 +108,47 @@ def test_cell_plan_edge_cases():
     assert pl.n_global == 7
     assert sdist.cell_level([-0.5, 0.5] * 3, 0.3) == 0
     assert sdist.cell_level([-0.5, 0.5] * 3, 0.0036) == 7
+
+
+@pytest.mark.parametrize("level,boundary,nranks,max_ring", [(2, [1, 1, 1], 3, 3), (3, [1, 0, 1], 4, 4), (3, [0, 0, 0], 5, 2),
+                                                            (1, [1, 1, 1], 2, 2)])
+def test_cell_plan_rings_against_brute_force(level, boundary, nranks, max_ring):
+    """per-cell reach on small grids, where a reach of several rings wraps around the periodic box more than once: the
+    halo cells of every rank against the definition (non-empty foreign cells within rings[c] rings, Chebyshev distance
+    with the minimum image on periodic axes, of an own non-empty cell c), and what a rank sends against what its peers
+    expect"""
+    side = 1 << level
+    ncell = side ** 3
+    rng = np.random.default_rng(level * 10 + nranks)
+    # cell index of every grid position (the cells are Hilbert-ordered)
+    g = (np.arange(side) + 0.5) / side - 0.5
+    gx, gy, gz = (a.ravel() for a in np.meshgrid(g, g, g, indexing="ij"))
+    keys = host.hilbert_keys(gx, gy, gz, [-0.5, 0.5] * 3, boundary)
+    cell = (keys >> np.uint64(3 * (21 - level))).astype(np.int64)
+    pos = np.zeros((ncell, 3), np.int64)
+    ijk = np.stack(np.meshgrid(np.arange(side), np.arange(side), np.arange(side), indexing="ij"), -1).reshape(-1, 3)
+    pos[cell] = ijk
+    G = rng.integers(0, 9, ncell).astype(np.uint32)
+    G[rng.random(ncell) < 0.25] = 0
+    rings = rng.integers(1, max_ring + 1, ncell).astype(np.uint8)
+    plans = [sdist.cell_plan(G, level, boundary, r, nranks, rings=rings) for r in range(nranks)]
+    sp = plans[0].cell_splits.astype(np.int64)
+    owner = np.searchsorted(sp[1:-1], np.arange(ncell), side="right")
+    d = np.abs(pos[:, None, :] - pos[None, :, :])
+    for k in range(3):
+        if boundary[k] == 1:
+            d[:, :, k] = np.minimum(d[:, :, k], side - d[:, :, k])
+    cheb = d.max(-1)  # cheb[c, c2]
+    nonempty = G > 0
+    for r, pl in enumerate(plans):
+        own = (owner == r) & nonempty
+        need = ((cheb <= rings[:, None]) & own[:, None] & nonempty[None, :] & (owner != r)[None, :]).any(0)
+        np.testing.assert_array_equal(pl.recv_cells, np.nonzero(need)[0])
+        assert pl.n_halo_left + pl.n_halo_right == int(G[need].sum())
+        # send lists: cell c of rank r goes to rank q iff some non-empty cell of q has c within its reach
+        for k, q in enumerate(pl.peers):
+            wants = ((cheb <= rings[:, None]) & ((owner == q) & nonempty)[:, None]).any(0) & own
+            n_send = int(pl.send_offsets[k + 1] - pl.send_offsets[k])
+            assert n_send == int(G[wants].sum()), (r, q)
+            kk = np.nonzero(plans[q].peers == r)[0]
+            assert kk.size == 1 and int(plans[q].recv_count[kk[0]]) == n_send
