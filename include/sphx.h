@@ -86,7 +86,7 @@ extern "C"
         const float*  vy;
         const float*  vz;
         const double* temp;
-        const double* u; /* internal energy; used instead of temp when temp == NULL (hydro_ve/eos.hpp:66-91) */
+        const double* u; /* internal energy; when non-NULL it is used INSTEAD of temp (hydro_ve/eos.hpp:71 `d.u.empty()`, eos_gpu.cu:55) */
         unsigned*     nc; /* out: 1 + neighbour count (find_neighbors.hpp:26,36) */
         float*        xm;
         float*        kx;
@@ -297,6 +297,9 @@ extern "C"
 
 #define SPHX_SYNC_PRESORTED 1 /* x, y, z are in SFC order already: keys are computed, nothing is sorted, order may be NULL */
 #define SPHX_SYNC_NO_TREE 2   /* keys and SFC order only; the tree buffers may be NULL */
+#define SPHX_SYNC_LIMIT_SHRINK 4 /* a->box is the box of the PREVIOUS sync: open dimensions follow the particles but a side
+                                    moves inwards by at most 5 % of the previous extent (limitBoxShrinking, sfc/box.hpp:397-414,
+                                    applied by the reference on every sync but the first, domain/assignment.hpp:80-82) */
 
     size_t sphx_domain_sync_bytes(size_t n, int maxNodes);
 
@@ -308,7 +311,8 @@ extern "C"
      * (sfc/box.hpp:318-334). When boxOut != NULL the limits of the non-periodic dimensions are first recomputed as the
      * coordinate extrema (makeGlobalBox, sfc/box_mpi.hpp:66-109) and the box that was used is returned there; with
      * boxOut == NULL a->box is used as given. Fields are NOT moved here: apply `order` with sphx_reorder_fields. Returns
-     * the node counts (host); synchronises the stream. SPHX_ERR_WORKSPACE if the tree needs more than maxNodes nodes. */
+     * the node counts (host); synchronises the stream. SPHX_ERR_WORKSPACE if the tree needs more than maxNodes nodes.
+     * n == 0 (a rank without particles) is not an error: nothing is sorted and the tree is the empty root leaf. */
     int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodes, int* numLeafNodes);
 
     /* counts[c] = number of keys in Hilbert cell c of `level` (8^level cells, cell = key >> 3 (21 - level)) for SFC-sorted

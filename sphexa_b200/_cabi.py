@@ -102,6 +102,7 @@ class SphxTurbulenceSettings(C.Structure):
 
 
 UNIQUE_ID_BYTES = 128
+SPHX_SYNC_PRESORTED, SPHX_SYNC_NO_TREE, SPHX_SYNC_LIMIT_SHRINK = 1, 2, 4
 
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
 

@@ -394,8 +394,37 @@ int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodesOut, i
     if (!noTree && (!a->childOffsets || !a->internalToLeaf || !a->levelRange || !a->leaves || !a->layout ||
                     !a->centers || !a->sizes || !a->prefixes))
         return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: null tree buffer");
-    if (a->n == 0 || a->n >= (size_t(1) << 31)) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: bad particle count");
+    if (a->n >= (size_t(1) << 31)) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: bad particle count");
     if (!noTree && a->maxNodes < 9) return syncFail(SPHX_ERR_INVALID, "sphx_domain_sync: maxNodes too small");
+    if (a->n == 0)
+    {
+        // a rank without particles (more ranks than occupied cells): nothing to sort; the tree is the empty root leaf
+        cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+        if (boxOut) *boxOut = a->box;
+        if (!noTree)
+        {
+            const SphxBox& b = a->box;
+            const int      lr[23] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+            const uint64_t lv[2] = {0, uint64_t(1) << 63}, pre = 1;
+            const unsigned lay[2] = {0, 0};
+            const int      zero   = 0;
+            double         ctr[3], sz[3];
+            for (int d = 0; d < 3; ++d)
+                ctr[d] = 0.5 * (b.lim[2 * d] + b.lim[2 * d + 1]), sz[d] = 0.5 * (b.lim[2 * d + 1] - b.lim[2 * d]);
+            SYNC_CUDA(cudaMemcpyAsync(a->levelRange, lr, sizeof(lr), cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->leaves, lv, sizeof(lv), cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->prefixes, &pre, 8, cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->layout, lay, sizeof(lay), cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->childOffsets, &zero, 4, cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->internalToLeaf, &zero, 4, cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->centers, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaMemcpyAsync(a->sizes, sz, sizeof(sz), cudaMemcpyHostToDevice, st));
+            SYNC_CUDA(cudaStreamSynchronize(st));
+        }
+        if (numNodesOut) *numNodesOut = noTree ? 0 : 1;
+        if (numLeafNodesOut) *numLeafNodesOut = noTree ? 0 : 1;
+        return SPHX_OK;
+    }
     SyncScratch s(a->n, a->maxNodes);
     if (a->scratchBytes < s.total)
         return syncFail(SPHX_ERR_WORKSPACE, "sphx_domain_sync: scratch too small, need " + std::to_string(s.total));
@@ -420,7 +449,18 @@ int sphx_domain_sync(const SphxSyncArgs* a, SphxBox* boxOut, int* numNodesOut, i
         SYNC_CUDA(cudaMemcpyAsync(res, ext, sizeof(res), cudaMemcpyDeviceToHost, stream));
         SYNC_CUDA(cudaStreamSynchronize(stream));
         for (int d = 0; d < 3; ++d)
-            if (box.boundary[d] != 1) box.lim[2 * d] = fromOrderedBits(res[2 * d]), box.lim[2 * d + 1] = fromOrderedBits(res[2 * d + 1]);
+        {
+            if (box.boundary[d] == 1) continue;
+            double lo = fromOrderedBits(res[2 * d]), hi = fromOrderedBits(res[2 * d + 1]);
+            if (a->flags & SPHX_SYNC_LIMIT_SHRINK)
+            {
+                // limitBoxShrinking (sfc/box.hpp:397-414; domain/assignment.hpp:80-82): after the first sync a side of
+                // the box moves inwards by at most 5 % of the previous extent
+                const double pl = a->box.lim[2 * d], ph = a->box.lim[2 * d + 1], ext = ph - pl;
+                lo = std::min(lo, pl + 0.05 * ext), hi = std::max(hi, ph - 0.05 * ext);
+            }
+            box.lim[2 * d] = lo, box.lim[2 * d + 1] = hi;
+        }
     }
     if (boxOut) *boxOut = box;
 

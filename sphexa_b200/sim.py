@@ -327,6 +327,7 @@ class Simulation(HydroData):
         self.f["id"] = torch.arange(n, dtype=torch.int64, device=dev)
         self.spare = {k: torch.empty_like(self.f[k]) for k in self.SYNC_FIELDS}
         self.bucket_size = bucket_size
+        self._synced_once = False
         self.keys = torch.zeros(n, dtype=torch.int64, device=dev)
         self.order = torch.zeros(n, dtype=torch.int32, device=dev)
         self._alloc_tree(max(4096, n // 4))
@@ -353,6 +354,8 @@ class Simulation(HydroData):
                 setattr(a, k, getattr(t, k).data_ptr())
             a.scratch, a.scratchBytes = self.sync_scratch.data_ptr(), self.sync_scratch.numel()
             a.stream = self.stream.cuda_stream if self.stream is not None else None
+            # every sync but the first limits how fast an open box may shrink (domain/assignment.hpp:80-82)
+            a.flags = _cabi.SPHX_SYNC_LIMIT_SHRINK if self._synced_once else 0
             nn, nl, box = C.c_int(0), C.c_int(0), _cabi.SphxBox()
             rc = self.L.sphx_domain_sync(C.byref(a), C.byref(box), C.byref(nn), C.byref(nl))
             if rc == 4 and t.max_nodes < 8 * self.n + 64:  # SPHX_ERR_WORKSPACE: grow the tree buffers
@@ -361,6 +364,7 @@ class Simulation(HydroData):
             _cabi.check(rc)
             t.num_nodes, t.num_leaves = nn.value, nl.value
             self.box_lim = [float(v) for v in box.lim]  # open dimensions follow the particles (makeGlobalBox)
+            self._synced_once = True
             break
         names = self.SYNC_FIELDS
         src = (C.c_void_p * len(names))(*[self.f[k].data_ptr() for k in names])

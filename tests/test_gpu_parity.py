@@ -288,6 +288,28 @@ def test_block_search_with_coincident_particles(sx, oracle):
     assert (nc == 200).sum() == 400  # 199 coincident partners + self
 
 
+def test_eos_prefers_u_over_temp(sx):
+    """a dataset holding BOTH u and temp takes pressure and sound speed from u (hydro_ve/eos.hpp:71 `d.u.empty()`,
+    eos_gpu.cu:55 `u == nullptr`); temp is only used when u is absent"""
+    import torch
+    d = load_golden("turb12_step0.npz")
+    got, hd = run_step_by_loops(sx, d)
+    prho_t, c_t = hd.get("prho").copy(), hd.get("c").copy()
+    cv = np.float32(np.float64(np.float32(8.317e7) / np.float32(hd.p.muiConst)) / (hd.p.gamma - 1.0))
+    u = np.float64(cv) * hd.get("temp")
+    hd.f["u"] = torch.from_numpy(2.0 * u).to(hd.device)           # u says "twice as hot" as temp
+    hd.eos()
+    np.testing.assert_allclose(hd.get("prho"), 2.0 * prho_t, rtol=2e-7)
+    np.testing.assert_allclose(hd.get("c"), np.sqrt(2.0) * c_t, rtol=2e-7)
+    hd.f["u"] = torch.from_numpy(u).to(hd.device)
+    hd.eos()
+    np.testing.assert_allclose(hd.get("prho"), prho_t, rtol=2e-7)
+    del hd.f["u"]
+    hd.eos()
+    np.testing.assert_array_equal(hd.get("prho"), prho_t)
+    np.testing.assert_array_equal(hd.get("c"), c_t)
+
+
 def test_edge_cases(sx):
     """empty range, ragged last group, ngmax truncation semantics, error codes"""
     d = load_golden("turb12_step0.npz")

@@ -60,6 +60,46 @@ def device_sync(sx, x, y, z, box, boundary, bucket=64, update_box=False):
     return out
 
 
+def test_domain_sync_shrink_limit_and_empty_rank(sx):
+    """open box: SPHX_SYNC_LIMIT_SHRINK keeps each side within 5 % of the previous extent (limitBoxShrinking,
+    sfc/box.hpp:397-414; domain/assignment.hpp:80-82); n == 0 is a no-op with the empty root leaf as tree"""
+    import torch
+    from sphexa_b200 import _cabi, host
+    from sphexa_b200.sim import DeviceTree
+    L = _cabi.load()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    n = 4000
+    pts = 0.3 + 0.4 * rng.random((3, n))
+    pts[0] = -0.2 + 1.4 * rng.random(n)  # x leaves the previous box on both sides: the box grows freely
+    xd, yd, zd = (torch.from_numpy(pts[d].copy()).to(dev) for d in range(3))
+    t = DeviceTree.empty(n, dev)
+    keys = torch.zeros(n, dtype=torch.int64, device=dev)
+    order = torch.zeros(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(L.sphx_domain_sync_bytes(n, n), dtype=torch.uint8, device=dev)
+
+    def run(count, flags, boundary):
+        a = _cabi.SphxSyncArgs()
+        a.n, a.box, a.bucketSize = count, host.make_box([0., 1.] * 3, boundary), 64
+        a.x, a.y, a.z = xd.data_ptr(), yd.data_ptr(), zd.data_ptr()
+        a.keys, a.order, a.maxNodes = keys.data_ptr(), order.data_ptr(), n
+        for k in ("prefixes", "childOffsets", "internalToLeaf", "levelRange", "leaves", "layout", "centers", "sizes"):
+            setattr(a, k, getattr(t, k).data_ptr())
+        a.scratch, a.scratchBytes, a.flags = scratch.data_ptr(), scratch.numel(), flags
+        nn, nl, bo = C.c_int(0), C.c_int(0), _cabi.SphxBox()
+        _cabi.check(L.sphx_domain_sync(C.byref(a), C.byref(bo), C.byref(nn), C.byref(nl)))
+        return list(bo.lim), nn.value, nl.value
+
+    fit = [pts[0].min(), pts[0].max(), pts[1].min(), pts[1].max(), pts[2].min(), pts[2].max()]
+    box, _, _ = run(n, 0, [0, 0, 1])
+    assert box == [fit[0], fit[1], fit[2], fit[3], 0.0, 1.0]          # first call: the fitting box; z is periodic
+    box, _, _ = run(n, _cabi.SPHX_SYNC_LIMIT_SHRINK, [0, 0, 1])
+    assert box == [fit[0], fit[1], 0.05, 0.95, 0.0, 1.0]              # y may shrink by 5 % per side only
+    box, nn, nl = run(0, 0, [0, 0, 0])
+    assert (nn, nl) == (1, 1) and box == [0., 1.] * 3
+    assert t.childOffsets[0].item() == 0 and t.layout[:2].tolist() == [0, 0]
+
+
 def assert_tree_equal(got: dict, ht):
     exp = ht.as_dump_dict()
     assert got["tree_childOffsets"].size == exp["tree_childOffsets"].size
