@@ -220,7 +220,9 @@ extern "C"
     int sphx_iad_divv_curlv(const SphxStepArgs* a, SphxStepResult* r);
     /* sph::cuda::computeAVswitches (hydro_ve/av_switches_gpu.cu:48-99): alpha in/out */
     int sphx_av_switches(const SphxStepArgs* a);
-    /* sph::cuda::computeMomentumEnergy<avClean> (hydro_ve/momentum_energy_gpu.cu:54-144): ax, ay, az, du, r->minDtCourant */
+    /* sph::cuda::computeMomentumEnergy<avClean> (hydro_ve/momentum_energy_gpu.cu:54-144): ax, ay, az, du, r->minDtCourant.
+     * With r != NULL the call also returns the search's sticky error status of this step (SPHX_ERR_TRAVERSAL, ...), so a
+     * caller that issues the loops one by one without synchronising learns of it at the end of the step. */
     int sphx_momentum_energy(const SphxStepArgs* a, SphxStepResult* r);
 
     /* halo exchange callback used by sphx_hydro_step between the loops: exchange the `count` listed device arrays
@@ -569,6 +571,12 @@ extern "C"
     /* sphx_hydro_step with the four halo exchanges of HydroVeProp::computeForces (ve_hydro.hpp:154,165,174,185) done
      * by sphx_halo_exchange and the result scalars reduced over all ranks (min dt, sum of neighbours, max nc). */
     int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* comm, const SphxHaloPlan* plan, SphxStepResult* r);
+
+    /* the reductions at the end of a distributed step on their own, for callers that issue the loops one by one:
+     * MIN of minDtCourant / minDtRho (ts_global.hpp:97-113), SUM of totalNeighbors, MAX of maxNc, and the agreement on
+     * the status: every rank passes its local status; if any rank failed, every rank gets an error back. One grouped
+     * NCCL all-reduce; synchronises the stream. */
+    int sphx_reduce_step_result(SphxComm* comm, int localStatus, SphxStepResult* inout, void* stream);
 
     /* sph::updateH (sph/include/sph/kernels.hpp:26-32), T = float: host evaluation of exactly the arithmetic the
      * device uses (bit-exact emulation of glibc powf, csrc/sphx_powf.h), exported for verification against libm. */

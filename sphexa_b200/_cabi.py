@@ -117,7 +117,7 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_debug_candidate_chunk", 
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
            "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
-           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
+           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_reduce_step_result", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
            "sphx_cell_plan_device_bytes", "sphx_cell_plan_build_device",
            "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
@@ -176,6 +176,7 @@ def load():
     L.sphx_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.sphx_hydro_step_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_reduce_step_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.sphx_domain_sync_bytes.restype = C.c_size_t
     L.sphx_domain_sync_bytes.argtypes = [C.c_size_t, C.c_int]
     L.sphx_domain_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

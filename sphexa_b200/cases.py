@@ -48,8 +48,8 @@ def _finish(sx, x, y, z, box_lim, boundary, p: Params, fields: dict, device, buc
     return hd
 
 
-def sedov_fields(x, y, z, p: Params, r1=0.5, mTotal=1.0, width=0.1, u0=1e-8, energyTotal=1.0):
-    n = x.size
+def sedov_fields(x, y, z, p: Params, r1=0.5, mTotal=1.0, width=0.1, u0=1e-8, energyTotal=1.0, n_total=None):
+    n = x.size if n_total is None else n_total
     totalVolume = (2 * r1) ** 3
     hInit = np.cbrt(3.0 / (4 * np.pi) * p.ng0 * totalVolume / n) * 0.5
     ener0 = energyTotal / np.pi ** 1.5 / 1.0 / width ** 3.0
@@ -60,12 +60,27 @@ def sedov_fields(x, y, z, p: Params, r1=0.5, mTotal=1.0, width=0.1, u0=1e-8, ene
                 temp=ui / np.float64(cv), alpha=np.float32(p.alphamin))
 
 
-def sedov_global(side: int) -> dict:
+def regular_grid_slice(r: float, side: int, b: int, e: int):
+    """particles [b, e) of regular_grid (generation order: z-major, x fastest) without building the whole lattice"""
+    step = (2.0 * r) / side
+    c = (-r + 0.5 * step) + np.arange(side, dtype=np.float64) * step
+    idx = np.arange(b, e, dtype=np.int64)
+    return c[idx % side].copy(), c[(idx // side) % side].copy(), c[idx // (side * side)].copy()
+
+
+def sedov_global(side: int, part: tuple[int, int] | None = None) -> dict:
     """host-side description of the Sedov case (positions in generation order, per-particle fields, box, params):
-    input of dist.DistributedHydro"""
+    input of dist.DistributedHydro / dist.DistributedSimulation. part = (rank, nranks): only that rank's contiguous slice
+    of the generation order is built (a 400^3 lattice is 64 M particles; no rank needs all of it)."""
     p = Params(minDt=1e-6, minDt_m1=1e-6, gamma=5.0 / 3.0, muiConst=10.0)
-    x, y, z = regular_grid(0.5, side)
-    return dict(x=x, y=y, z=z, fields=sedov_fields(x, y, z, p), params=p, box=[-0.5, 0.5] * 3, boundary=[1, 1, 1])
+    n = side ** 3
+    if part is None:
+        x, y, z = regular_grid(0.5, side)
+        return dict(x=x, y=y, z=z, fields=sedov_fields(x, y, z, p), params=p, box=[-0.5, 0.5] * 3, boundary=[1, 1, 1])
+    b, e = part[0] * n // part[1], (part[0] + 1) * n // part[1]
+    x, y, z = regular_grid_slice(0.5, side, b, e)
+    return dict(x=x, y=y, z=z, fields=sedov_fields(x, y, z, p, n_total=n), params=p, box=[-0.5, 0.5] * 3,
+                boundary=[1, 1, 1], slice=(b, e), n_global=n)
 
 
 def noh_global(side: int) -> dict:

@@ -255,9 +255,12 @@ int sphx_momentum_energy(const SphxStepArgs* a, SphxStepResult* r)
     SPHX_CUDA(sphx::launchMomentumEnergy(*a, w.layout, s));
     if (r)
     {
+        // the last loop of the step: its scalars are the step's, and the sticky error flags of the search (traversal
+        // overflow, h-iteration, ngmax, candidate space) are reported here for callers that issued the loops one by one
         sphx::StepScalars h;
         if (int rc = readScalars(w, s, h)) return rc;
         fillResult(h, a->p, r);
+        return errFlagsToStatus(h.errFlags);
     }
     return SPHX_OK;
 }
@@ -283,24 +286,49 @@ int sphx_hydro_step(const SphxStepArgs* a, SphxHaloExchangeFn halo, void* haloUs
         return rc ? fail(SPHX_ERR_NCCL, "halo exchange callback failed") : SPHX_OK;
     };
 
+    // Everything the six loops REQUIRE is checked before the first exchange, so that argument errors (the same on
+    // every rank of a multi-GPU step) never leave a peer waiting in a receive. A failure that shows up later on one
+    // rank only (CUDA launch error) skips that rank's remaining loops but NOT its remaining exchanges: the collectives
+    // of all ranks stay matched, and the caller's reduction of the status (sphx_reduce_step_result) reports it.
+    if (int rc = checkTree(a->tree)) return rc;
+    if (a->p.ng0 > a->p.ngmax) return fail(SPHX_ERR_INVALID, "ng0 should be smaller than ngmax");
+    REQUIRE(f.x); REQUIRE(f.y); REQUIRE(f.z); REQUIRE(f.h); REQUIRE(f.nc); REQUIRE(f.m); REQUIRE(f.xm); REQUIRE(a->wh);
+    REQUIRE(a->whd); REQUIRE(f.kx); REQUIRE(f.gradh); REQUIRE(f.prho); REQUIRE(f.c); REQUIRE(f.vx); REQUIRE(f.vy);
+    REQUIRE(f.vz); REQUIRE(f.c11); REQUIRE(f.c12); REQUIRE(f.c13); REQUIRE(f.c22); REQUIRE(f.c23); REQUIRE(f.c33);
+    REQUIRE(f.divv); REQUIRE(f.alpha); REQUIRE(f.ax); REQUIRE(f.ay); REQUIRE(f.az); REQUIRE(f.du);
+    if (a->p.eosChoice == 0 && !f.temp && !f.u) return fail(SPHX_ERR_INVALID, "ideal gas EOS needs temp or u");
+    if (a->p.eosChoice < 0 || a->p.eosChoice > 2) return fail(SPHX_ERR_INVALID, "unknown eosChoice");
+    if (a->p.avClean)
+    {
+        REQUIRE(f.dV11); REQUIRE(f.dV12); REQUIRE(f.dV13); REQUIRE(f.dV22); REQUIRE(f.dV23); REQUIRE(f.dV33);
+    }
+
+    int         status = SPHX_OK;
+    std::string firstError;
+    auto        stage = [&](int rc)
+    {
+        if (rc && !status) status = rc, firstError = g_lastError;
+    };
+
     // ve_hydro.hpp:147-190
-    if (int rc = sphx_find_neighbors_xmass(a, nullptr)) return rc;
+    stage(sphx_find_neighbors_xmass(a, nullptr));
     if (int rc = exchange({{f.xm, 4}})) return rc;
-    if (int rc = sphx_ve_def_gradh(a)) return rc;
-    if (int rc = sphx_eos(a)) return rc;
+    if (!status) stage(sphx_ve_def_gradh(a));
+    if (!status) stage(sphx_eos(a));
     if (int rc = exchange({{(void*)f.vx, 4}, {(void*)f.vy, 4}, {(void*)f.vz, 4}, {f.prho, 4}, {f.c, 4}, {f.kx, 4}}))
         return rc;
-    if (int rc = sphx_iad_divv_curlv(a, nullptr)) return rc;
+    if (!status) stage(sphx_iad_divv_curlv(a, nullptr));
     if (int rc = exchange({{f.c11, 4}, {f.c12, 4}, {f.c13, 4}, {f.c22, 4}, {f.c23, 4}, {f.c33, 4}, {f.divv, 4}}))
         return rc;
-    if (int rc = sphx_av_switches(a)) return rc;
+    if (!status) stage(sphx_av_switches(a));
     if (a->p.avClean)
     {
         if (int rc = exchange({{f.dV11, 4}, {f.dV12, 4}, {f.dV13, 4}, {f.dV22, 4}, {f.dV23, 4}, {f.dV33, 4}, {f.alpha, 4}}))
             return rc;
     }
     else if (int rc = exchange({{f.alpha, 4}})) { return rc; }
-    if (int rc = sphx_momentum_energy(a, nullptr)) return rc;
+    if (!status) stage(sphx_momentum_energy(a, nullptr));
+    if (status) return fail(status, firstError);
 
     if (r)
     {

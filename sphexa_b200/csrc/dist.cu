@@ -336,34 +336,47 @@ int distHaloCallback(void* user, int count, void* const* arrays, const int* elem
 }
 } // namespace
 
-int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* c, const SphxHaloPlan* plan, SphxStepResult* r)
+int sphx_reduce_step_result(SphxComm* c, int localStatus, SphxStepResult* r, void* stream)
 {
-    if (!a || !c || !plan) return SPHX_ERR_INVALID;
-    DistCtx        ctx{c, plan, a->stream};
-    SphxStepResult local;
-    int            rc = sphx_hydro_step(a, distHaloCallback, &ctx, &local);
-    // the global reductions must run on every rank, also when this rank's step failed
-    double mins[2] = {rc ? 0.0 : local.minDtCourant, rc ? 0.0 : local.minDtRho};
-    double sums[2] = {rc ? 0.0 : double(local.totalNeighbors), rc ? 1.0 : 0.0};
-    double maxs[2] = {rc ? 0.0 : double(local.maxNc), rc ? 0.0 : double(local.numHIterated)};
-    int    rc2     = sphx_allreduce_f64(c, mins, 2, 0, a->stream);
-    if (!rc2) rc2 = sphx_allreduce_f64(c, sums, 2, 2, a->stream);
-    if (!rc2) rc2 = sphx_allreduce_f64(c, maxs, 1, 1, a->stream);
+    if (!c || !r) return SPHX_ERR_INVALID;
+    const int rc = localStatus;
+    // ONE all-reduce for everything: MIN of {dtCourant, dtRho, -maxNc, -failed}, SUM of the neighbour count
+    // (as two 2^26-limbs, exact in double). Runs on every rank, also when this rank's step failed.
+    const unsigned long tn = rc ? 0ul : r->totalNeighbors;
+    double v[6] = {rc ? 0.0 : r->minDtCourant, rc ? 0.0 : r->minDtRho, rc ? 0.0 : -double(r->maxNc), rc ? -1.0 : 0.0,
+                   double(tn & ((1ul << 26) - 1)), double(tn >> 26)};
+    auto   s    = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(c->scratch, v, sizeof(v), cudaMemcpyHostToDevice, s) != cudaSuccess) return SPHX_ERR_CUDA;
+    SPHX_NCCL(c->api->GroupStart());
+    SPHX_NCCL(c->api->AllReduce(c->scratch, c->scratch, 4, ncclDouble, ncclMin, c->comm, s));
+    SPHX_NCCL(c->api->AllReduce(c->scratch + 4, c->scratch + 4, 2, ncclDouble, ncclSum, c->comm, s));
+    SPHX_NCCL(c->api->GroupEnd());
+    if (cudaMemcpyAsync(v, c->scratch, sizeof(v), cudaMemcpyDeviceToHost, s) != cudaSuccess) return SPHX_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return SPHX_ERR_CUDA;
     if (rc) return rc;
-    if (rc2) return rc2;
-    if (sums[1] != 0.0)
+    if (v[3] != 0.0)
     {
         g_distError = "the hydro step failed on another rank";
         return SPHX_ERR_NCCL;
     }
-    if (r)
-    {
-        r->minDtCourant   = mins[0];
-        r->minDtRho       = mins[1];
-        r->totalNeighbors = (unsigned long)(sums[0]);
-        r->maxNc          = unsigned(maxs[0]);
-        r->numHIterated   = local.numHIterated;
-    }
+    r->minDtCourant   = v[0];
+    r->minDtRho       = v[1];
+    r->maxNc          = unsigned(-v[2]);
+    r->totalNeighbors = (unsigned long)(v[4]) + ((unsigned long)(v[5]) << 26);
+    return SPHX_OK;
+}
+
+int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* c, const SphxHaloPlan* plan, SphxStepResult* r)
+{
+    if (!a || !c || !plan) return SPHX_ERR_INVALID;
+    DistCtx        ctx{c, plan, a->stream};
+    SphxStepResult local{};
+    // sphx_hydro_step rejects bad arguments before its first exchange and, after a later local failure, still runs its
+    // remaining exchanges; the reduction below then runs on every rank and carries the failure to all of them
+    int rc = sphx_hydro_step(a, distHaloCallback, &ctx, &local);
+    int rc2 = sphx_reduce_step_result(c, rc, &local, a->stream);
+    if (rc2) return rc2;
+    if (r) *r = local;
     return SPHX_OK;
 }
 

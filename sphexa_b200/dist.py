@@ -367,15 +367,23 @@ class DistributedSimulation:
         self.box_lim = [float(v) for v in glob["box"]]
         self.boundary = [int(b) for b in glob["boundary"]]
         self.p = glob["params"]
-        n = glob["x"].size
+        # initial distribution: a contiguous slice of the particles in GENERATION order; the first sync migrates them.
+        # `glob` holds either all particles or (glob["slice"] = (b, e), glob["n_global"]) just this rank's slice.
+        if "slice" in glob:
+            n, (b, e) = int(glob["n_global"]), glob["slice"]
+            assert (b, e) == (rank * n // nranks, (rank + 1) * n // nranks) and glob["x"].size == e - b
+            lo = b
+        else:
+            n = glob["x"].size
+            b, e = rank * n // nranks, (rank + 1) * n // nranks
+            lo = 0
         self.n_global = n
-        # initial distribution: a contiguous slice of the particles in GENERATION order; the first sync migrates them
-        b, e = rank * n // nranks, (rank + 1) * n // nranks
         f = glob["fields"]
+        n_have = glob["x"].size
 
         def chunk(name, dtype):
             v = f.get(name, 0.0) if name not in ("x", "y", "z") else glob[name]
-            a = v[b:e] if isinstance(v, np.ndarray) and v.shape == (n,) else np.full(e - b, v)
+            a = v[b - lo:e - lo] if isinstance(v, np.ndarray) and v.shape == (n_have,) else np.full(e - b, v)
             return torch.from_numpy(np.ascontiguousarray(a, dtype)).to(self.dev)
 
         self.cur = {k: chunk(k, np.float64 if k in ("x", "y", "z", "temp") else np.float32)
