@@ -961,6 +961,32 @@ void orc_momentum_energy_jloop_d(int avClean, unsigned i, double K, const OrcBox
     out[0] = a[0], out[1] = a[1], out[2] = a[2], out[3] = du, out[4] = mv;
 }
 
+/* The momentum/energy loop over a whole particle range with T = double (neighbour list in the CPU layout,
+ * nb[i * ngmax + k], nc including self as the reference stores it): what the reference computes when every operation
+ * is carried out in fp64 on the same inputs. The spread between this and the production fp32 evaluation is the
+ * reference's OWN rounding / summation noise; tests use it to set the comparison floors of du, ax, ay, az. */
+void orc_momentum_energy_fields_d(unsigned first, unsigned last, unsigned ngmax, double K, const OrcBox* b,
+                                  const unsigned* nb, const unsigned* nc, const double* x, const double* y,
+                                  const double* z, const double* vx, const double* vy, const double* vz, const double* h,
+                                  const double* m, const double* prho, const double* c, const double* c11,
+                                  const double* c12, const double* c13, const double* c22, const double* c23,
+                                  const double* c33, double Atmin, double Atmax, double ramp, const double* wh,
+                                  const double* kx, const double* xm, const double* alpha, double* ax, double* ay,
+                                  double* az, double* du)
+{
+    Box box(b);
+#pragma omp parallel for schedule(static)
+    for (unsigned i = first; i < last; ++i)
+    {
+        double   a[3], dui, mv;
+        unsigned cnt = std::min(nc[i - first] - 1, ngmax);
+        momentumEnergyJLoop<false, double>(i, K, box, nb + size_t(i - first) * ngmax, cnt, x, y, z, vx, vy, vz, h, m,
+                                           prho, c, c11, c12, c13, c22, c23, c33, Atmin, Atmax, ramp, wh, kx, xm, alpha,
+                                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, a, &dui, &mv);
+        ax[i - first] = a[0], ay[i - first] = a[1], az[i - first] = a[2], du[i - first] = dui;
+    }
+}
+
 /* --- turbulence stirring ------------------------------------------------------------------------------------------- */
 
 // stirring.hpp:106-125 (loop over the groups' particles) with stirParticle :45-83; Tc = T = double, Ta = float

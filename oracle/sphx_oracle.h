@@ -133,6 +133,17 @@ extern "C"
                                        const double* dV13, const double* dV22, const double* dV23, const double* dV33,
                                        double* out /* ax ay az du maxvsignal */);
 
+    /* momentum/energy loop over [first, last) with every operation in fp64 (the all-double instantiation of
+     * momentum_energy_kern.hpp:65-222) on the CPU neighbour-list layout; outputs indexed from `first` */
+    void orc_momentum_energy_fields_d(unsigned first, unsigned last, unsigned ngmax, double K, const OrcBox* box,
+                                      const unsigned* neighbors, const unsigned* nc, const double* x, const double* y,
+                                      const double* z, const double* vx, const double* vy, const double* vz,
+                                      const double* h, const double* m, const double* prho, const double* c,
+                                      const double* c11, const double* c12, const double* c13, const double* c22,
+                                      const double* c23, const double* c33, double Atmin, double Atmax, double ramp,
+                                      const double* wh, const double* kx, const double* xm, const double* alpha,
+                                      double* ax, double* ay, double* az, double* du);
+
     /* --- turbulence stirring (sph/include/sph/hydro_turb/) ----------------------------------------------------------- */
     /* sph::computeStirring (stirring.hpp:106-125) with stirParticle (:45-83), Tc = T = double, Ta = float */
     void orc_compute_stirring(unsigned first, unsigned last, const double* x, const double* y, const double* z,

@@ -154,3 +154,30 @@ def hydro_step_f(d: dict, wh=None, whd=None) -> dict:
     return dict(h=h, nc=nc, neighbors=nb, xm=xm, kx=kx, gradh=gradh, prho=prho, c=c, c11=c11, c12=c12, c13=c13,
                 c22=c22, c23=c23, c33=c33, divv=divv, curlv=curlv, alpha=alpha, ax=ax, ay=ay, az=az, du=du,
                 dts=np.array([dtCour.value, dtRho.value]), fails=fails, wh=wh, whd=whd, K=prm.K)
+
+
+def momentum_fields_d(d: dict) -> dict:
+    """ax, ay, az, du of a reference dump re-evaluated with EVERY operation in fp64 (the all-double instantiation of
+    momentum_energy_kern.hpp:65-222) from the dump's own inputs of that loop (h, nc, neighbours, prho, c, c11..c33, kx,
+    xm, alpha as the reference stored them, widened to double). |dump - this| is the reference's own fp32 rounding and
+    summation noise on these fields."""
+    L = lib()
+    n = int(d["n"][0])
+    ngmax = int(d["ngmax"][0])
+    v = d["params"]
+    box = make_box(d["box"], d["boundary"])
+    wh, _, _ = tables_d()
+    # the production table is float: use ITS values (widened), so that only the arithmetic differs, not the inputs
+    wh = d["wh"].astype(np.float64) if "wh" in d else tables_f()[0].astype(np.float64)
+    dd = {k: np.ascontiguousarray(d[k], np.float64) for k in ("x", "y", "z", "vx", "vy", "vz", "h", "m", "prho", "c", "c11",
+                                                             "c12", "c13", "c22", "c23", "c33", "kx", "xm", "alpha")}
+    nb = np.ascontiguousarray(d["neighbors"], np.uint32)
+    nc = np.ascontiguousarray(d["nc"], np.uint32)
+    out = {k: np.zeros(n, np.float64) for k in ("ax", "ay", "az", "du")}
+    D = C.c_double
+    L.orc_momentum_energy_fields_d(C.c_uint(0), C.c_uint(n), C.c_uint(ngmax), D(v[0]), C.byref(box), P(nb), P(nc),
+                                   *[P(dd[k]) for k in ("x", "y", "z", "vx", "vy", "vz", "h", "m", "prho", "c", "c11", "c12",
+                                                        "c13", "c22", "c23", "c33")],
+                                   D(np.float32(v[10])), D(np.float32(v[11])), D(np.float32(v[12])), P(wh), P(dd["kx"]),
+                                   P(dd["xm"]), P(dd["alpha"]), P(out["ax"]), P(out["ay"]), P(out["az"]), P(out["du"]))
+    return out
