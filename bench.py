@@ -100,7 +100,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("SPHX_BENCH_CLOCK_MS", "100"), "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -365,13 +366,14 @@ def field_errors(got: dict, ref: dict) -> dict:
     return out
 
 
-def dist_parity(sx, rank, world, dev, dist, tol=1e-4) -> list:
+def dist_parity(sx, rank, world, dev, dist, tol=2e-4) -> list:
     """N ranks vs rank 0 alone, by particle id (SURVEY 8e "parity without MPI"; the reference's own multi-rank tests are
     domain/test/integration_mpi/exchange_halos_gpu.cpp and domain_nranks.cpp:64-131): one mid-size case per BASELINE
     family goes through the dynamic decomposition (migration, halo discovery, local tree) and the distributed hydro step
-    on all ranks, and through the plain single-GPU path on rank 0. nc and h must be identical, the 18 fp32 fields agree to
-    `tol` (summation order differs with the local candidate numbering), the reduced scalars agree; two more steps
-    follow to compare the evolving energies."""
+    on all ranks, and through the plain single-GPU path on rank 0. nc and h must be identical and the reduced scalars
+    agree. The 18 fp32 fields are two evaluations by the SAME kernels with different block boundaries (hence block
+    origins and summation order): each is within 1e-4 of the reference (tests/test_gpu_parity.py), so they are held to
+    2e-4 of each other, with the floors of that test. Two more steps follow to compare the evolving energies."""
     import numpy as np
     import torch
     rows = []
@@ -513,7 +515,7 @@ def our_arm(args):
     ev = [(mk(), [mk() for _ in range(len(call_names) + 1)], mk(), mk()) for _ in range(K)]
     nstat = []
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get("SPHX_BENCH_CLOCK_MS") != "0":
         sampler.start()
     if world > 1:
         dist.barrier()
@@ -529,6 +531,26 @@ def our_arm(args):
     clocks = sampler.stop() if rank == 0 else None
 
     forces_ms = [e[1][0].elapsed_time(e[1][-1]) for e in ev]
+    static_after_ms = None
+    if not args.no_static and world == 1:
+        # the same frozen-state repetitions once more, now on the evolved state and a warm GPU: separates what the
+        # evolution costs from what the clocks do
+        hd = run.hd
+        run.sync()
+        h1, a1 = hd.f["h"].clone(), hd.f["alpha"].clone()
+        reps = []
+        for k in range(6):
+            hd.f["h"].copy_(h1)
+            hd.f["alpha"].copy_(a1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run.forces()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            reps.append(e0.elapsed_time(e1))
+        hd.f["h"].copy_(h1)
+        hd.f["alpha"].copy_(a1)
+        static_after_ms = sum(reps[1:]) / 5
     phase_ms = {}
     for i, name in enumerate(call_names):
         phase_ms[name] = phase_ms.get(name, 0.0) + sum(e[1][i].elapsed_time(e[1][i + 1]) for e in ev) / K
@@ -550,6 +572,11 @@ def our_arm(args):
              "minDtCourant": res.minDtCourant, "minDtRho": res.minDtRho, "minDt": run.p.minDt, "ttot": run.p.ttot,
              "etot": cons.etot, "ecin": cons.ecin, "eint": cons.eint,
              "h_iterated_last_step": nstat[-1][2], "static_ms_per_step": static_ms,
+             "static_ms_per_step_evolved_state": static_after_ms, "ms_all_steps": [round(v, 3) for v in forces_ms],
+             "phases_ms_slowest_step": {n: round(ev[forces_ms.index(max(forces_ms))][1][i].elapsed_time(
+                 ev[forces_ms.index(max(forces_ms))][1][i + 1]), 3) for i, n in enumerate(call_names)},
+             "phases_ms_fastest_step": {n: round(ev[forces_ms.index(min(forces_ms))][1][i].elapsed_time(
+                 ev[forces_ms.index(min(forces_ms))][1][i + 1]), 3) for i, n in enumerate(call_names)},
              "static_note": "round-1 definition, kept for continuity: the frozen initial state, h and alpha restored "
                             "before every repetition"}
 

@@ -568,6 +568,62 @@ extern "C"
     int sphx_exchange_slices(SphxComm* comm, const size_t* sendOffsets, const size_t* recvOffsets, int count,
                              const void* const* src, void* const* dst, const int* elemBytes, void* stream);
 
+    /* rank and size of a communicator */
+    int sphx_comm_rank(const SphxComm* comm, int* rank, int* nranks);
+
+    /* --- multi-rank Domain::sync behind one entry point ------------------------------------ */
+
+    /* cstone::Domain (domain/include/cstone/domain/domain.hpp:60-160) as far as the hot path needs it: the global box,
+     * the bucket size of the local octree, the communicator, and the state one sync leaves for the next calls (halo plan,
+     * octree arrays, scratch). comm == NULL: one rank. */
+    typedef struct SphxDomain SphxDomain;
+    int  sphx_domain_create(SphxDomain** out, SphxComm* comm, const SphxBox* box, unsigned bucketSize);
+    void sphx_domain_destroy(SphxDomain* d);
+
+    typedef struct SphxDomainSyncArgs
+    {
+        int          count;     /* 4 <= count <= 16 particle arrays: [0..2] x, y, z (double), [3] h (float), then the
+                                   conserved fields of the propagator (4 or 8 bytes per particle) */
+        void* const* arrays;    /* DEVICE arrays of `capacity` elements; this rank's particles sit at [inFirst, inLast) */
+        void* const* spare;     /* DEVICE arrays of the same shapes: the sync works array -> spare -> array -> spare,
+                                   like the reference swaps its fields with scratch vectors (domain.hpp:224-230) */
+        const int*   elemBytes;
+        size_t       capacity;
+        size_t       inFirst, inLast;
+        int          numHaloFields; /* <= 8 */
+        const int*   haloFields;    /* indices into arrays: fields whose halo values the sync delivers (the reference:
+                                       x, y, z, h always, plus m in ve_hydro.hpp:133-139) */
+        void*        stream;
+    } SphxDomainSyncArgs;
+
+    typedef struct SphxDomainResult
+    {
+        size_t          first, last; /* Domain::startIndex / endIndex: the assigned particles in the new layout */
+        size_t          numLocal;    /* Domain::nParticlesWithHalos: [halos | assigned | halos], SFC-sorted */
+        size_t          numGlobal;
+        size_t          needCapacity; /* set also on SPHX_ERR_WORKSPACE: elements per array the sync needs */
+        SphxBox         box;          /* Domain::box(): open dimensions follow the particles */
+        SphxTreeView    tree;         /* Domain::octreeProperties(): arrays owned by the domain, valid until the next sync */
+        const uint64_t* localKeys;    /* Hilbert keys of the numLocal particles (device, owned by the domain) */
+        int             level;        /* cell level of the decomposition plan */
+        int             swapped;      /* 1: the new local set is in `spare`, the caller swaps its pointers */
+    } SphxDomainResult;
+
+    /* cstone::Domain::sync (domain/domain.hpp:181-234) for N ranks, re-designed around the global per-cell particle
+     * histogram (csrc/domain_dist.cu): box update, keys + radix sort, histogram + ncclAllReduce, decomposition plan on the
+     * device, particle migration (one slice per peer and field), merge, halo exchange of `haloFields`, octree over the
+     * local particles. Collective over the communicator; every rank must call it. On SPHX_ERR_WORKSPACE nothing has moved:
+     * grow the arrays to res->needCapacity (keeping [inFirst, inLast)) and call again (every rank: the error is NOT agreed
+     * upon across ranks, size the arrays with head room). Synchronises the stream. */
+    int sphx_domain_sync_dist(SphxDomain* d, const SphxDomainSyncArgs* a, SphxDomainResult* res);
+
+    /* Domain::exchangeHalos (domain/domain.hpp:372-377) with the plan of the last sync */
+    int sphx_domain_exchange_halos(SphxDomain* d, int count, void* const* arrays, const int* elemBytes, void* stream);
+    /* the halo plan of the last sync, for sphx_hydro_step_dist */
+    const SphxHaloPlan* sphx_domain_halo_plan(const SphxDomain* d);
+    /* copy the Hilbert keys of the numLocal particles of the last sync into a caller buffer (device) */
+    int sphx_domain_copy_local_keys(const SphxDomain* d, uint64_t* dst_dev, void* stream);
+
     /* sphx_hydro_step with the four halo exchanges of HydroVeProp::computeForces (ve_hydro.hpp:154,165,174,185) done
      * by sphx_halo_exchange and the result scalars reduced over all ranks (min dt, sum of neighbours, max nc). */
     int sphx_hydro_step_dist(const SphxStepArgs* a, SphxComm* comm, const SphxHaloPlan* plan, SphxStepResult* r);

@@ -34,6 +34,27 @@ namespace sph
 //! 128 targets over [firstBody, lastBody) and uses the GroupView for that range only
 unsigned nsGroupSize() { return 32; }
 
+//! uniform SFC-consecutive target groups for the consumers of the GroupView outside the hot path (see
+//! integration/include/sph/groups.hpp, the shadow of sph/groups.hpp that calls this instead of the group splitter)
+__global__ void uniformGroupsKernel(cstone::LocalIndex first, cstone::LocalIndex last, unsigned groupSize,
+                                    cstone::LocalIndex numEntries, cstone::LocalIndex* data)
+{
+    cstone::LocalIndex k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < numEntries)
+    {
+        unsigned long long v = (unsigned long long)(first) + (unsigned long long)(k) * groupSize;
+        data[k] = v < last ? cstone::LocalIndex(v) : last;
+    }
+}
+
+void sphxUniformGroups(cstone::LocalIndex first, cstone::LocalIndex last, unsigned groupSize,
+                       cstone::DeviceVector<cstone::LocalIndex>& data)
+{
+    cstone::LocalIndex numGroups = (last - first + groupSize - 1) / groupSize;
+    reallocate(data, size_t(numGroups) + 1, 1.01);
+    uniformGroupsKernel<<<(numGroups + 256) / 256, 256>>>(first, last, groupSize, numGroups + 1, rawPtr(data));
+}
+
 namespace cuda
 {
 namespace

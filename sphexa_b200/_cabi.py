@@ -53,6 +53,18 @@ class SphxHaloPlan(C.Structure):
                 ("sendBufferBytes", C.c_size_t)]
 
 
+class SphxDomainSyncArgs(C.Structure):
+    _fields_ = [("count", C.c_int), ("arrays", C.c_void_p), ("spare", C.c_void_p), ("elemBytes", C.c_void_p),
+                ("capacity", C.c_size_t), ("inFirst", C.c_size_t), ("inLast", C.c_size_t), ("numHaloFields", C.c_int),
+                ("haloFields", C.c_void_p), ("stream", C.c_void_p)]
+
+
+class SphxDomainResult(C.Structure):
+    _fields_ = [("first", C.c_size_t), ("last", C.c_size_t), ("numLocal", C.c_size_t), ("numGlobal", C.c_size_t),
+                ("needCapacity", C.c_size_t), ("box", SphxBox), ("tree", SphxTreeView), ("localKeys", C.c_void_p),
+                ("level", C.c_int), ("swapped", C.c_int)]
+
+
 class SphxSyncArgs(C.Structure):
     _fields_ = [("n", C.c_size_t), ("box", SphxBox), ("bucketSize", C.c_uint), ("x", C.c_void_p), ("y", C.c_void_p),
                 ("z", C.c_void_p), ("keys", C.c_void_p), ("order", C.c_void_p), ("maxNodes", C.c_int),
@@ -117,7 +129,7 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_debug_candidate_chunk", 
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
            "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
-           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_reduce_step_result", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
+           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_reduce_step_result", "sphx_comm_rank", "sphx_domain_create", "sphx_domain_destroy", "sphx_domain_sync_dist", "sphx_domain_exchange_halos", "sphx_domain_halo_plan", "sphx_domain_copy_local_keys", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
            "sphx_cell_plan_device_bytes", "sphx_cell_plan_build_device",
            "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
@@ -177,6 +189,15 @@ def load():
     L.sphx_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.sphx_hydro_step_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_reduce_step_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.sphx_comm_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_domain_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    L.sphx_domain_destroy.argtypes = [C.c_void_p]
+    L.sphx_domain_destroy.restype = None
+    L.sphx_domain_sync_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_domain_exchange_halos.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sphx_domain_halo_plan.argtypes = [C.c_void_p]
+    L.sphx_domain_halo_plan.restype = C.c_void_p
+    L.sphx_domain_copy_local_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_domain_sync_bytes.restype = C.c_size_t
     L.sphx_domain_sync_bytes.argtypes = [C.c_size_t, C.c_int]
     L.sphx_domain_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -194,6 +194,14 @@ int sphx_comm_init(SphxComm** out, int rank, int nranks, const char* id128)
     return SPHX_OK;
 }
 
+int sphx_comm_rank(const SphxComm* c, int* rank, int* nranks)
+{
+    if (!c) return SPHX_ERR_INVALID;
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return SPHX_OK;
+}
+
 int sphx_comm_free(SphxComm* c)
 {
     if (!c) return SPHX_OK;

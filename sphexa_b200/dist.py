@@ -340,22 +340,33 @@ def init_comm(L, rank: int, nranks: int, device, pg=None):
     return comm
 
 
+class _DomainTree:
+    """OctreeNsView arrays owned by a SphxDomain (valid until its next sync)"""
+
+    def __init__(self, view: _cabi.SphxTreeView):
+        self._view = _cabi.SphxTreeView()
+        C.memmove(C.byref(self._view), C.byref(view), C.sizeof(view))
+        self.num_nodes, self.num_leaves = view.numNodes, view.numLeafNodes
+
+    def view(self) -> _cabi.SphxTreeView:
+        return self._view
+
+
 class DistributedSimulation:
     """One rank of the multi-GPU time-step loop: the reference's main loop (sphexa.cpp:141-170) with a dynamic SFC
     domain decomposition redone in every sync().
 
-    sync() = multi-rank Domain::sync (domain/domain.hpp:181-234) re-designed around ONE global object, the particle
-    count per Hilbert cell of a level whose cell edge is >= 2 max(h):
-      keys + local radix sort (device) -> cell histogram (device) -> ncclAllReduce -> host plan (assignment, halo
-      cells, send lists, layout: sphx_cell_plan_build_host, no request messages) -> particle migration as one slice
-      per peer and field (sphx_exchange_slices) -> merge sort of the arrivals -> halo exchange of x, y, z, h, m ->
-      octree over the local particles (sphx_domain_sync, presorted).
-    The reference negotiates the same things through a focus octree with peer-to-peer messages.
-    `pg`: torch.distributed group for host-side plumbing only (unique id, the R x R matrix of migration counts)."""
+    sync() = sphx_domain_sync_dist (csrc/domain_dist.cu): multi-rank Domain::sync (domain/domain.hpp:181-234) re-designed
+    around ONE global object, the particle count per Hilbert cell of a level whose cell edge is >= 2 max(h):
+      keys + local radix sort -> cell histogram -> ncclAllReduce -> decomposition plan on the device (assignment, halo
+      cells, send lists, layout; no request messages) -> particle migration as one slice per peer and field -> merge of
+      the arrivals -> halo exchange of x, y, z, h, m -> octree over the local particles.
+    The reference negotiates the same things through a focus octree with peer-to-peer messages. This class only owns the
+    torch tensors (fields and their spares) and swaps them as the C call says; nothing on the data path runs in Python.
+    `pg`: torch.distributed group for host-side plumbing only (the NCCL unique id)."""
 
     SYNC_FIELDS = ("x", "y", "z", "h", "m", "vx", "vy", "vz", "x_m1", "y_m1", "z_m1", "du_m1", "temp", "alpha", "id")
     HALO_SYNC_FIELDS = ("x", "y", "z", "h", "m")
-    MAX_EXCHANGE_ARRAYS = 7
 
     def __init__(self, sim, glob: dict, rank: int, nranks: int, device, pg=None, bucket: int = 64):
         import torch
@@ -386,221 +397,98 @@ class DistributedSimulation:
             a = v[b - lo:e - lo] if isinstance(v, np.ndarray) and v.shape == (n_have,) else np.full(e - b, v)
             return torch.from_numpy(np.ascontiguousarray(a, dtype)).to(self.dev)
 
-        self.cur = {k: chunk(k, np.float64 if k in ("x", "y", "z", "temp") else np.float32)
-                    for k in self.SYNC_FIELDS if k != "id"}
+        init = {k: chunk(k, np.float64 if k in ("x", "y", "z", "temp") else np.float32)
+                for k in self.SYNC_FIELDS if k != "id"}
         if "vx" in f:  # x_m1 = v * minDt (noh_init.hpp:99-101); zero for Sedov
             for k, v in (("x_m1", "vx"), ("y_m1", "vy"), ("z_m1", "vz")):
-                self.cur[k] = (self.cur[v].double() * self.p.minDt).float()
-        self.cur["id"] = torch.arange(b, e, dtype=torch.int64, device=self.dev)
-        self.comm = init_comm(self.L, rank, nranks, device, pg)
+                init[k] = (init[v].double() * self.p.minDt).float()
+        init["id"] = torch.arange(b, e, dtype=torch.int64, device=self.dev)
+        self.comm = init_comm(self.L, rank, nranks, device, pg) if nranks > 1 else C.c_void_p()
+        self.domain = C.c_void_p()
+        box = host.make_box(self.box_lim, self.boundary)
+        _cabi.check(self.L.sphx_domain_create(C.byref(self.domain), self.comm if nranks > 1 else None, C.byref(box),
+                                              bucket))
         self.hd = None
+        self._allocate(int(1.3 * (e - b)) + 4096, keep=(init, 0, e - b))
+        self._in = (0, e - b)  # where this rank's particles sit in the field arrays
         self.plan = None
         self.result = _cabi.SphxStepResult()
         self.conserved = _cabi.SphxConserved()
         self.cons_scratch = torch.zeros(self.L.sphx_conserved_scratch_bytes(), dtype=torch.uint8, device=self.dev)
         self.iteration = 0
-        self.timings = {}
-        self._plan_scratch = None
+        self.level = 0
         self.turbulence = None  # set to a sim.Turbulence for the turbulence-ve propagator
-        self.profile = None  # set to a dict to accumulate per-stage wall times of sync() (synchronises the device)
 
-    # -- helpers ------------------------------------------------------------------------------------------------------
-    def _allreduce_host(self, values, op):
-        a = np.ascontiguousarray(values, np.float64)
-        if self.nranks > 1:
-            _cabi.check(self.L.sphx_allreduce_f64(self.comm, _p(a), a.size, op, None))
-        return a
-
-    def _sfc_sort(self, x, y, z, presorted=False, tree=None):
-        """keys (+ SFC permutation, + tree) of n particles through sphx_domain_sync"""
+    # -- memory -------------------------------------------------------------------------------------------------------
+    def _allocate(self, capacity: int, keep=None):
+        """field arrays + spares of `capacity` particles (and the step workspace for as many assigned particles); `keep`
+        = (arrays, first, last): particles to carry over into [0, last - first) of the new arrays"""
         import torch
-        n = x.numel()
-        keys = torch.empty(n, dtype=torch.int64, device=self.dev)
-        order = torch.empty(n, dtype=torch.int32, device=self.dev)
-        max_nodes = tree.max_nodes if tree is not None else 0
-        scratch = torch.empty(self.L.sphx_domain_sync_bytes(n, max_nodes), dtype=torch.uint8, device=self.dev)
-        a = _cabi.SphxSyncArgs()
-        a.n, a.box, a.bucketSize = n, host.make_box(self.box_lim, self.boundary), self.bucket
-        a.x, a.y, a.z = x.data_ptr(), y.data_ptr(), z.data_ptr()
-        a.keys, a.order, a.maxNodes = keys.data_ptr(), order.data_ptr(), max_nodes
-        if tree is not None:
-            for k in ("prefixes", "childOffsets", "internalToLeaf", "levelRange", "leaves", "layout", "centers",
-                      "sizes"):
-                setattr(a, k, getattr(tree, k).data_ptr())
-        a.scratch, a.scratchBytes = scratch.data_ptr(), scratch.numel()
-        a.flags = (1 if presorted else 0) | (2 if tree is None else 0)
-        nn, nl = C.c_int(0), C.c_int(0)
-        rc = self.L.sphx_domain_sync(C.byref(a), None, C.byref(nn), C.byref(nl))
-        if tree is not None and rc == 0:
-            tree.num_nodes, tree.num_leaves = nn.value, nl.value
-        return rc, keys, order
-
-    def _reorder(self, order, src: dict, dst: dict, n: int):
-        names = list(src)
-        k = len(names)
-        _cabi.check(self.L.sphx_reorder_fields(order.data_ptr(), n, k,
-                                               (C.c_void_p * k)(*[src[m].data_ptr() for m in names]),
-                                               (C.c_void_p * k)(*[dst[m].data_ptr() for m in names]),
-                                               (C.c_int * k)(*[src[m].element_size() for m in names]), None))
+        hd = self.sim.HydroData(capacity, 0, capacity, self.box_lim, self.boundary, self.p, device=self.dev)
+        for name in ("x_m1", "y_m1", "z_m1", "du_m1"):
+            hd.f[name] = torch.zeros(capacity, dtype=torch.float32, device=self.dev)
+        hd.f["id"] = torch.zeros(capacity, dtype=torch.int64, device=self.dev)
+        if keep is not None:
+            src, b, e = keep
+            for k in self.SYNC_FIELDS:
+                hd.f[k][:e - b].copy_(src[k][b:e])
+        if self.hd is not None:
+            hd.n, hd.first, hd.last, hd.tree = self.hd.n, self.hd.first, self.hd.last, self.hd.tree
+        self.hd = hd
+        self.spare = {k: torch.empty_like(hd.f[k]) for k in self.SYNC_FIELDS}
+        self.capacity = capacity
 
     # -- Domain::sync -------------------------------------------------------------------------------------------------
     def sync(self):
-        import torch
-
-        L, R, me = self.L, self.nranks, self.rank
-        cur = self.cur
-        n_old = cur["x"].numel()
-        prof = self.profile
-
-        def tick(name):
-            # stage timing (profile runs only: synchronises the device)
-            if prof is not None:
-                torch.cuda.synchronize()
-                now = time.perf_counter()
-                prof[name] = prof.get(name, 0.0) + now - self._t0
-                self._t0 = now
-
-        if prof is not None:
-            torch.cuda.synchronize()
-            self._t0 = time.perf_counter()
-        # global box: open dimensions follow the particles (makeGlobalBox, box_mpi.hpp:66-109)
-        if any(b != 1 for b in self.boundary):
-            lo = [float(cur[k].min()) if n_old else np.inf for k in "xyz"]
-            hi = [float(cur[k].max()) if n_old else -np.inf for k in "xyz"]
-            lo, hi = self._allreduce_host(lo, 0), self._allreduce_host(hi, 1)
-            for d in range(3):
-                if self.boundary[d] != 1:
-                    self.box_lim[2 * d], self.box_lim[2 * d + 1] = float(lo[d]), float(hi[d])
-        h_max = float(self._allreduce_host([float(cur["h"].max()) if n_old else 0.0], 1)[0])
-        h_sum = self._allreduce_host([float(cur["h"].sum()) if n_old else 0.0, float(n_old)], 2)
-        h_mean = h_sum[0] / max(h_sum[1], 1.0)
-        # cells RING_LEVELS finer than the coarsest level whose edge is >= 2 max(h); a cell reaches ceil(2 h_cell / edge)
-        # rings of cells, h_cell = largest h in the cell over all ranks. With (nearly) uniform smoothing lengths the
-        # finer cells buy nothing (same reach, 64 x more cells to scan): one ring of the coarse cells then.
-        coarse = cell_level(self.box_lim, h_max)
-        level = min(7, coarse + (RING_LEVELS if h_max > 1.25 * h_mean else 0))
-        ncell = 8 ** level
-        edge = min(self.box_lim[2 * d + 1] - self.box_lim[2 * d] for d in range(3)) / (1 << level)
-        max_ring = max(1, min(16, int(math.ceil(2.0 * h_max * 1.0001 / edge))))
-        tick("box_hmax")
-
-        # 1. local SFC order, cell histogram, global histogram
-        rc, keys, order = self._sfc_sort(cur["x"], cur["y"], cur["z"])
-        _cabi.check(rc)
-        tick("keys_sort")
-        hist = torch.zeros(ncell, dtype=torch.int32, device=self.dev)
-        _cabi.check(L.sphx_cell_histogram(keys.data_ptr(), n_old, level, hist.data_ptr(), None))
-        local_hist = hist
-        if R > 1:
-            local_hist = hist.clone()
-            _cabi.check(L.sphx_allreduce_device(self.comm, hist.data_ptr(), ncell, 0, 2, None))
-        # largest h per cell (this rank, then all ranks) -> reach of the cell in rings
-        hcell = torch.zeros(ncell, dtype=torch.float32, device=self.dev)
-        if n_old:
-            cell_of = (keys >> (3 * (21 - level))).to(torch.int64)
-            hcell.scatter_reduce_(0, cell_of, cur["h"][order.to(torch.int64)], reduce="amax", include_self=True)
-        if R > 1:
-            _cabi.check(L.sphx_allreduce_device(self.comm, hcell.data_ptr(), ncell, 2, 1, None))
-        rings = torch.ceil(hcell.double() * (2.0 * 1.0001 / edge)).clamp_(1, max_ring).to(torch.uint8)
-        tick("histogram_allreduce")
-
-        # 2. plan on the device: assignment, halo cells, send lists, layout; only the summary POD comes to the host
-        cp, send_idx, self._plan_scratch = cell_plan_device(hist, local_hist, level, self.boundary, me, R,
-                                                            scratch=self._plan_scratch,
-                                                            send_capacity=4 * n_old + 65536, rings=rings,
-                                                            max_ring=max_ring)
-        tick("device_plan")
-        send_off = cp.send_off_local  # my sorted particles [send_off[r], send_off[r+1]) belong to rank r
-        send_cnt = np.diff(send_off)
-        if R > 1:
-            # R x R matrix of migration counts: every rank fills its row, one all-reduce completes it
-            m = torch.zeros(R * R, dtype=torch.int64, device=self.dev)
-            m[me * R:(me + 1) * R] = torch.from_numpy(send_cnt.astype(np.int64)).to(self.dev)
-            _cabi.check(L.sphx_allreduce_device(self.comm, m.data_ptr(), R * R, 1, 2, None))
-            recv_cnt = m.view(R, R)[:, me].cpu().numpy().astype(np.int64)
-        else:
-            recv_cnt = send_cnt.copy()
-        recv_off = np.concatenate([[0], np.cumsum(recv_cnt)])
-        n_new = int(recv_off[-1])
-        assert n_new == cp.n_assigned, (n_new, cp.n_assigned)
-        tick("counts_allgather")
-
-        # 3. migration: sort my particles, ship one slice per peer and field, merge-sort what arrived
-        sorted_ = {k: torch.empty_like(cur[k]) for k in self.SYNC_FIELDS}
-        self._reorder(order, cur, sorted_, n_old)
-        if R > 1:
-            arrived = {k: torch.empty(n_new, dtype=cur[k].dtype, device=self.dev) for k in self.SYNC_FIELDS}
-            so = np.ascontiguousarray(send_off, np.uint64)
-            ro = np.ascontiguousarray(recv_off, np.uint64)
-            names = list(self.SYNC_FIELDS)
-            k = len(names)
-            _cabi.check(L.sphx_exchange_slices(self.comm, _p(so), _p(ro), k,
-                                               (C.c_void_p * k)(*[sorted_[m].data_ptr() for m in names]),
-                                               (C.c_void_p * k)(*[arrived[m].data_ptr() for m in names]),
-                                               (C.c_int * k)(*[sorted_[m].element_size() for m in names]), None))
-            rc, _, order2 = self._sfc_sort(arrived["x"], arrived["y"], arrived["z"])
-            _cabi.check(rc)
-        else:
-            arrived, order2 = sorted_, None
-        tick("migrate_sort")
-
-        # 4. local arrays [halos | assigned | halos]
-        n_local, first, last = cp.n_local, cp.n_halo_left, cp.n_halo_left + cp.n_assigned
-        if self.hd is None or n_local > self.cap_local or cp.n_assigned > self.cap_assigned:
-            self.cap_local, self.cap_assigned = int(1.2 * n_local) + 1024, int(1.2 * cp.n_assigned) + 1024
-            hd = self.sim.HydroData(self.cap_local, 0, self.cap_assigned, self.box_lim, self.boundary, self.p,
-                                    device=self.dev)
-            for name in ("x_m1", "y_m1", "z_m1", "du_m1"):
-                hd.f[name] = torch.zeros(self.cap_local, dtype=torch.float32, device=self.dev)
-            hd.f["id"] = torch.zeros(self.cap_local, dtype=torch.int64, device=self.dev)
-            hd.tree = self.sim.DeviceTree.empty(max(4096, self.cap_local // 4), self.dev)
-            self.hd = hd
-        hd = self.hd
-        hd.n, hd.first, hd.last = n_local, first, last
-        hd.box_lim = list(self.box_lim)
-        dstv = {k: hd.f[k][first:last] for k in self.SYNC_FIELDS}
-        if order2 is not None:
-            self._reorder(order2, arrived, dstv, n_new)
-        else:
-            for k in self.SYNC_FIELDS:
-                dstv[k].copy_(arrived[k])
-        self.cur = dstv  # views into the local arrays: integrate() updates them in place
-        tick("layout_reorder")
-
-        # 5. halo plan on the device, halo exchange of the fields the search and the first loop read
-        self._send_idx = send_idx
-        nsend = cp.num_send
-        buf_bytes = self.MAX_EXCHANGE_ARRAYS * ((nsend * 8 + 15) // 16 * 16) + 64
-        self._send_buf = torch.empty(buf_bytes, dtype=torch.uint8, device=self.dev)
-        self._plan_host = cp  # keeps the host arrays alive
-        pl = _cabi.SphxHaloPlan()
-        pl.numPeers = cp.peers.size
-        pl.peers, pl.sendOffsets = cp.peers.ctypes.data, cp.send_offsets.ctypes.data
-        pl.sendIdx = self._send_idx.data_ptr()
-        pl.recvBegin, pl.recvCount = cp.recv_begin.ctypes.data, cp.recv_count.ctypes.data
-        pl.sendBuffer, pl.sendBufferBytes = self._send_buf.data_ptr(), buf_bytes
-        self.plan = pl
-        if R > 1:
-            self.exchange(list(self.HALO_SYNC_FIELDS))
-        tick("halo_exchange")
-
-        # 6. octree over the local particles (already in SFC order)
+        L, names = self.L, self.SYNC_FIELDS
+        k = len(names)
+        halo = (C.c_int * len(self.HALO_SYNC_FIELDS))(*[names.index(h) for h in self.HALO_SYNC_FIELDS])
+        res = _cabi.SphxDomainResult()
         while True:
-            rc, lkeys, _ = self._sfc_sort(hd.f["x"][:n_local], hd.f["y"][:n_local], hd.f["z"][:n_local], presorted=True,
-                                          tree=hd.tree)
-            if rc == 4 and hd.tree.max_nodes < 8 * n_local + 64:
-                hd.tree = self.sim.DeviceTree.empty(2 * hd.tree.max_nodes, self.dev)
+            f = self.hd.f
+            a = _cabi.SphxDomainSyncArgs()
+            a.count = k
+            arrays = (C.c_void_p * k)(*[f[m].data_ptr() for m in names])
+            spare = (C.c_void_p * k)(*[self.spare[m].data_ptr() for m in names])
+            eb = (C.c_int * k)(*[f[m].element_size() for m in names])
+            a.arrays, a.spare, a.elemBytes = C.cast(arrays, C.c_void_p), C.cast(spare, C.c_void_p), C.cast(eb, C.c_void_p)
+            a.capacity, a.inFirst, a.inLast = self.capacity, self._in[0], self._in[1]
+            a.numHaloFields, a.haloFields = len(self.HALO_SYNC_FIELDS), C.cast(halo, C.c_void_p)
+            a.stream = None
+            rc = L.sphx_domain_sync_dist(self.domain, C.byref(a), C.byref(res))
+            if rc == 4:  # SPHX_ERR_WORKSPACE on every rank: nothing has moved, grow and call again
+                self._allocate(int(1.25 * max(res.needCapacity, self.capacity)) + 4096,
+                               keep=(f, self._in[0], self._in[1]))
+                self._in = (0, self._in[1] - self._in[0])
                 continue
             _cabi.check(rc)
             break
-        self.local_keys = lkeys
-        self.level = level
-        tick("local_tree")
+        if res.swapped:
+            for m in names:
+                self.hd.f[m], self.spare[m] = self.spare[m], self.hd.f[m]
+        hd = self.hd
+        hd.n, hd.first, hd.last = int(res.numLocal), int(res.first), int(res.last)
+        self.box_lim = [float(v) for v in res.box.lim]
+        hd.box_lim = list(self.box_lim)
+        hd.tree = _DomainTree(res.tree)
+        self._in = (hd.first, hd.last)
+        self.level = int(res.level)
+        self.plan = L.sphx_domain_halo_plan(self.domain)
+        self._local_keys_ptr = res.localKeys
+
+    @property
+    def local_keys(self):
+        """Hilbert keys of the local particles (copied out of the domain's buffer)"""
+        import torch
+        out = torch.empty(self.hd.n, dtype=torch.int64, device=self.dev)
+        _cabi.check(self.L.sphx_domain_copy_local_keys(self.domain, out.data_ptr(), None))
+        torch.cuda.synchronize(self.dev)
+        return out
 
     def exchange(self, names):
         arrs = (C.c_void_p * len(names))(*[self.hd.f[k].data_ptr() for k in names])
         eb = (C.c_int * len(names))(*[self.hd.f[k].element_size() for k in names])
-        _cabi.check(self.L.sphx_halo_exchange(self.comm, C.byref(self.plan), len(names), arrs, eb, None))
+        _cabi.check(self.L.sphx_domain_exchange_halos(self.domain, len(names), arrs, eb, None))
 
     # -- the rest of the loop ------------------------------------------------------------------------------------------
     def compute_forces(self):
@@ -608,7 +496,7 @@ class DistributedSimulation:
         holds the same stirring state (same seed, same time steps) and stirs its assigned particles"""
         a = self.hd.args()
         if self.nranks > 1:
-            _cabi.check(self.L.sphx_hydro_step_dist(C.byref(a), self.comm, C.byref(self.plan), C.byref(self.result)))
+            _cabi.check(self.L.sphx_hydro_step_dist(C.byref(a), self.comm, self.plan, C.byref(self.result)))
         else:
             _cabi.check(self.L.sphx_hydro_step(C.byref(a), None, None, C.byref(self.result)))
         if self.turbulence is not None:
@@ -652,6 +540,9 @@ class DistributedSimulation:
         return a.view(np.uint32) if name == "nc" else a
 
     def close(self):
+        if self.domain:
+            self.L.sphx_domain_destroy(self.domain)
+            self.domain = C.c_void_p()
         if self.comm:
             self.L.sphx_comm_free(self.comm)
             self.comm = C.c_void_p()

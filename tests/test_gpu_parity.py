@@ -35,11 +35,18 @@ def sx():
 FAMILIES = [("c11", "c12", "c13", "c22", "c23", "c33"), ("divv", "curlv"), ("ax", "ay", "az")]
 
 
-# du = K prho_i sum_j m_j a_mom (v_ij . A_ij) and a = -K sum_j (pressure-gradient pair terms): in near-uniform subsonic
-# flow (turbulence box: u = 1000, Mach 0.3) the ~100 pair terms cancel to < 1 % of their magnitude, and two fp32
-# evaluations that add them in a different order (the reference CPU's list order vs. our four interleaved partial sums)
-# differ by that summation noise. These fields get a floor of 1e-1 x the family max-norm, i.e. the absolute error allowed
-# for a nearly cancelled value is 1e-5 of the field scale (measured: 4e-6 du, 1.4e-6 ax).
+# du = K prho_i sum_j m_j a_mom (v_ij . A_ij) and a = -K sum_j (pressure-gradient pair terms): the ~100 pair terms of a
+# particle cancel to a few per cent of their magnitude (steep but smooth pressure field of the Sedov blob, near-uniform
+# subsonic turbulence), so ANY fp32 evaluation carries an absolute error that is a fixed fraction of the field scale,
+# whatever the value it belongs to. The reference's OWN production evaluation shows it: against the same loop carried
+# out in all-double on the same inputs (oracle.momentum_fields_d) it is off by up to 2.2e-6 x max|a| (Sedov 64^3),
+# 1.7e-6 (turbulence), 4.7e-6 x max|du|, i.e. up to 1.5e-2 RELATIVE for small values; the CUDA path is off by up to
+# 4.4e-6 x max|a| against the same all-double values (fp32 positions relative to the block origin instead of fp64
+# differences), and the two fp32 evaluations differ from each other by up to 5.5e-6 x scale
+# (profiles/r02_floor_analysis.json, tools/floor_analysis.py; test_floors_are_the_references_own_fp32_noise below keeps
+# the numbers honest). The floor of these four fields is therefore 1e-1 x the family max-norm: the absolute error allowed
+# for a nearly cancelled value is 1e-5 of the field scale, twice what two correct fp32 evaluations are observed to
+# differ by, and every value above a tenth of the scale is held to the plain 1e-4 relative tolerance.
 FLOOR_FRACTION = {"du": 1e-1, "ax": 1e-1, "ay": 1e-1, "az": 1e-1}
 
 
@@ -75,14 +82,42 @@ def run_step_by_loops(sx, d):
     return out, hd
 
 
-def check_against_reference(got, ref):
+CANCELLING = ("ax", "ay", "az", "du")
+
+
+def assert_within_reference_noise(got: dict, d: dict, oracle, tol=REL_TOL_F32, factor=3.0):
+    """du, ax, ay, az at resolutions where the pair terms cancel ever more strongly (the fp32 noise of these sums is a
+    fraction of the field scale that grows like width / h: 2e-6 of max|a| at Sedov 64^3, 4e-6 at 100^3 for the
+    reference itself): the yardstick is the all-double evaluation of the same loop on the reference's own inputs. The
+    CUDA value must be within 1e-4 relative of it, or within `factor` x the LARGEST error the reference's own fp32
+    evaluation makes against it on that field."""
+    exact = oracle.momentum_fields_d(d)
+    out = {}
+    for k in CANCELLING:
+        e, r32, g = exact[k], d[k].astype(np.float64), got[k].astype(np.float64)
+        noise = np.abs(r32 - e).max()
+        err = np.abs(g - e)
+        bad = err > np.maximum(tol * np.abs(e), factor * noise)
+        out[k] = (float(noise), float(err.max()))
+        assert not bad.any(), f"{k}: {int(bad.sum())} values off by more than {factor} x the reference's own fp32 noise " \
+                              f"{noise:.3e} (max err {err.max():.3e}, scale {np.abs(e).max():.3e})"
+    return out
+
+
+def check_against_reference(got, ref, oracle=None):
+    """oracle given: du / a are judged against the all-double values and the reference's own noise instead of the
+    fixed floors (assert_within_reference_noise)"""
     ngmax = int(ref["ngmax"][0])
     np.testing.assert_array_equal(got["h"], ref["h"])        # h-iteration trajectory bit-exact
     np.testing.assert_array_equal(got["nc"], ref["nc"])      # neighbour counts bit-exact
     off, idx = csr_sorted_neighbors(got["neighbors"], got["nc"], ngmax)
     np.testing.assert_array_equal(off, ref["nb_offsets"])
     np.testing.assert_array_equal(idx, ref["nb_sorted"])     # sorted neighbour sets bit-exact
-    assert_fields_close(got, ref)
+    if oracle is None:
+        assert_fields_close(got, ref)
+    else:
+        assert_fields_close(got, ref, [k for k in F32_FIELDS if k not in CANCELLING])
+        assert_within_reference_noise(got, ref, oracle)
     np.testing.assert_allclose(got["dts"], ref["dts"], rtol=1e-4)
     assert got["totalNeighbors"] == int(ref["nc"].astype(np.int64).sum())
 
@@ -155,6 +190,57 @@ def test_step_vs_compiled_reference(sx, tmp_path, case, n, steps, hs):
         d["nb_offsets"], d["nb_sorted"] = csr_sorted_neighbors(d["neighbors"], d["nc"], ngmax)
         got, _ = run_step_by_loops(sx, d)
         check_against_reference(got, d)
+
+
+@pytest.mark.skipif(not have_ref_harness(), reason="oracle/_ref/ref_harness not present")
+@pytest.mark.parametrize("case,n,steps", [("sedov", 100, 2), ("noh", 80, 1), ("turb", 64, 2)])
+def test_step_vs_compiled_reference_at_scale(sx, oracle, tmp_path, case, n, steps):
+    """the reference itself on 0.26 - 1 M particles: every target block runs in SHIFT mode (candidates moved to the
+    periodic image next to the block, the path the benchmark times; the 12^3 / 14^3 fixtures run in fold mode), and for
+    Sedov and turbulence the compared step is the one after the first integrate (v != 0, x off the lattice)"""
+    d = run_ref_harness(case, n, steps, tmp_path / "o", dump_every=1000)[-1]
+    assert d["_step"] == steps - 1
+    ngmax = int(d["ngmax"][0])
+    d["nb_offsets"], d["nb_sorted"] = csr_sorted_neighbors(d["neighbors"], d["nc"], ngmax)
+    got, hd = run_step_by_loops(sx, d)
+    assert int((hd.block_stats()["flags"] & 1).sum()) == 0  # no fold-mode block
+    check_against_reference(got, d, oracle)
+
+
+@pytest.mark.skipif(not have_ref_harness(), reason="oracle/_ref/ref_harness not present")
+def test_evolved_state_vs_compiled_reference(sx, tmp_path):
+    """BASELINE config 0 (sedov -n 50) after 100 steps of the REFERENCE: the blast wave has left the lattice behind
+    (neighbour counts vary, density contrasts at the shock, v of order one); the 101st hydro step field by field"""
+    d = run_ref_harness("sedov", 50, 101, tmp_path / "o", dump_every=100)[-1]
+    assert d["_step"] == 100
+    assert d["nc"].min() < 93 < d["nc"].max() and np.abs(d["vx"]).max() > 0.1
+    ngmax = int(d["ngmax"][0])
+    d["nb_offsets"], d["nb_sorted"] = csr_sorted_neighbors(d["neighbors"], d["nc"], ngmax)
+    got, _ = run_step_by_loops(sx, d)
+    check_against_reference(got, d)
+
+
+@pytest.mark.skipif(not have_ref_harness(), reason="oracle/_ref/ref_harness not present")
+@pytest.mark.parametrize("case,n,steps,hs", [("sedov", 64, 1, 1.0), ("turb", 32, 2, 1.4), ("noh", 40, 2, 1.0)])
+def test_floors_are_the_references_own_fp32_noise(sx, oracle, tmp_path, case, n, steps, hs):
+    """FLOOR_FRACTION of du / ax / ay / az is not a fudge: the all-double instantiation of the momentum loop on the
+    reference's own inputs (every operation in fp64) is the yardstick; the reference's production fp32 evaluation
+    misses it by `noise` (a fixed fraction of the field scale), the CUDA path by no more than 3 x that, and the absolute
+    error the floor admits (1e-4 x 1e-1 x scale) is within [2, 30] x the reference's own noise."""
+    d = run_ref_harness(case, n, steps, tmp_path / "o", dump_every=1000, hscale=hs)[-1]
+    exact = oracle.momentum_fields_d(d)
+    hd = sx.sim.from_dump(d)
+    hd.hydro_step()
+    fam = max(np.abs(exact[k]).max() for k in ("ax", "ay", "az"))
+    for k in ("ax", "ay", "az", "du"):
+        scale = np.abs(exact[k]).max() if k == "du" else fam
+        if scale == 0.0:
+            continue  # Sedov at t = 0: no energy rate
+        noise = np.abs(d[k].astype(np.float64) - exact[k]).max() / scale
+        err = np.abs(hd.get(k).astype(np.float64) - exact[k]).max() / scale
+        admitted = REL_TOL_F32 * FLOOR_FRACTION[k]
+        assert err <= 3.0 * noise, (case, k, err, noise)
+        assert 2.0 * noise <= admitted <= 30.0 * noise, (case, k, noise, admitted)
 
 
 @pytest.mark.parametrize("fname,chunk", [("noh14_step0.npz", 256), ("turb12_step0.npz", 320)])
