@@ -1,0 +1,67 @@
+"""The C++20 facade include/sphx_domain.hpp (cstone::Domain call shape: sync, exchangeHalos, startIndex/endIndex,
+nParticlesWithHalos, box, octreeProperties) driven by a C++ program (tests/cpp/domain_facade_test.cu), on one rank and on
+two (one process per GPU, NCCL id passed through a file), followed by the cstone::findNeighbors call shape on the synced
+arrays. The reference's counterpart is domain/test/integration_mpi/domain_nranks.cpp:64-131 (neighbour counts of randomly
+placed particles after Domain::sync, summed over ranks): here every particle's count is compared by id between the rank
+counts and against a brute-force search."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = Path(__file__).resolve().parent.parent
+EXE = REPO / "sphexa_b200" / "csrc" / "build" / "domain_facade_test"
+
+
+def _build():
+    if EXE.exists():
+        return
+    subprocess.run(["make", "-C", str(REPO / "sphexa_b200" / "csrc"), "build/domain_facade_test"], check=True)
+
+
+def _run(nranks, n, pbc, tmp):
+    idfile = tmp / f"id{nranks}"
+    outs = [tmp / f"out{nranks}_{r}.txt" for r in range(nranks)]
+    procs = [subprocess.Popen([str(EXE), str(r), str(nranks), str(idfile), str(outs[r]), str(n), str(pbc)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(nranks)]
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out
+    rows, heads = [], []
+    for o in outs:
+        lines = o.read_text().splitlines()
+        heads.append(dict(zip(lines[0].split()[0::2], map(int, lines[0].split()[1::2]))))
+        rows.append(np.array([ln.split() for ln in lines[1:]], dtype=np.float64).reshape(-1, 6))
+    return np.concatenate(rows), heads
+
+
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_domain_facade_one_and_two_ranks(tmp_path, pbc):
+    import torch
+    from scipy.spatial import cKDTree
+    _build()
+    n = 40000
+    one, h1 = _run(1, n, pbc, tmp_path)
+    assert h1[0]["n"] == n and h1[0]["local"] == n and h1[0]["global"] == n
+    ids = one[:, 0].astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.arange(n))
+    # brute force on the positions the driver reports (2 h_i spheres, self excluded; cstone::findNeighbors semantics)
+    o = np.argsort(ids)
+    pts, hh, cnt = one[o, 2:5], one[o, 5], one[o, 1].astype(np.int64)
+    tree = cKDTree(pts, boxsize=1.0 if pbc else None)
+    exp = np.array([len(v) - 1 for v in tree.query_ball_point(pts, 2.0 * hh * (1 - 1e-12))])
+    assert np.array_equal(cnt, exp)
+    assert 20 < cnt.mean() < 200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("the two-rank half needs 2 GPUs")
+    two, h2 = _run(2, n, pbc, tmp_path)
+    assert sum(h["n"] for h in h2) == n and all(h["local"] > h["n"] for h in h2)  # halos are there
+    ids2 = two[:, 0].astype(np.int64)
+    assert np.array_equal(np.sort(ids2), np.arange(n))   # every particle assigned to exactly one rank
+    o2 = np.argsort(ids2)
+    assert np.array_equal(two[o2, 1].astype(np.int64), cnt)  # neighbour counts by id: N ranks == 1 rank == brute force
+    assert np.array_equal(two[o2, 2:5], pts)
+    assert max(h["n"] for h in h2) < 0.6 * n                   # balanced
