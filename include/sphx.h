@@ -235,6 +235,89 @@ extern "C"
      * aliases them exactly as the reference does (ay->gradh, {gradh,az}->{divv,curlv}, {divv,curlv}->{ay,az}). */
     int sphx_hydro_step(const SphxStepArgs* a, SphxHaloExchangeFn halo, void* haloUser, SphxStepResult* r);
 
+    /* --- the all-double type set (north_star: "<= 1e-10 fp64") ---------------------------------------------------------- */
+
+    /* The same step with EVERY field and every operation in fp64: the instantiation the reference's own unit tests use
+     * (sph/test/ve.cpp: T = double) and its all-double build. This is the precision path (csrc/loops_f64.cu: one thread
+     * per target, pairs evaluated from the fp64 coordinates, per-pair PBC fold, four double pow in the Atwood ramp), not
+     * the fast one; it shares no pair code with the production path and serves as its on-device yardstick. One rank. */
+    typedef struct SphxFieldsF64
+    {
+        const double* x;
+        const double* y;
+        const double* z;
+        double*       h; /* in/out of the neighbour search */
+        const double* m;
+        const double* vx;
+        const double* vy;
+        const double* vz;
+        const double* temp;
+        const double* u; /* used instead of temp when non-NULL */
+        unsigned*     nc;
+        double*       xm;
+        double*       kx;
+        double*       gradh;
+        double*       prho;
+        double*       c;
+        double*       rho; /* optional outputs of the EOS */
+        double*       p;
+        double*       c11;
+        double*       c12;
+        double*       c13;
+        double*       c22;
+        double*       c23;
+        double*       c33;
+        double*       divv;
+        double*       curlv;
+        double*       alpha; /* in/out */
+        double*       ax;
+        double*       ay;
+        double*       az;
+        double*       du;
+        double*       dV11; /* avClean only */
+        double*       dV12;
+        double*       dV13;
+        double*       dV22;
+        double*       dV23;
+        double*       dV33;
+    } SphxFieldsF64;
+
+    typedef struct SphxParamsF64
+    {
+        double   K, Kcour, Krho, gamma, minDt, polytropic_const, polytropic_index, muiConst, soundSpeedConst, alphamin,
+            alphamax, decay_constant, Atmin, Atmax, ramp;
+        unsigned ng0, ngmax;
+        int      eosChoice, avClean;
+    } SphxParamsF64;
+
+    typedef struct SphxStepArgsF64
+    {
+        SphxFieldsF64 f;
+        size_t        numLocal, first, last;
+        SphxParamsF64 p;
+        SphxBox       box;
+        SphxTreeView  tree;
+        const double* wh;  /* 20000-entry kernel table in double (sphx_make_tables_host_f64), device */
+        const double* whd;
+        void*         workspace; /* device, sphx_workspace_bytes_f64(last - first, ngmax): the particle-index neighbour list */
+        size_t        workspaceBytes;
+        void*         stream;
+    } SphxStepArgsF64;
+
+    size_t sphx_workspace_bytes_f64(size_t numAssigned, unsigned ngmax);
+    /* createWharmonicTable<double> / createWharmonicDerivativeTable<double> (sph_kernel_tables.hpp:86-101,144-172) */
+    int sphx_make_tables_host_f64(double sincIndex, double* wh_host, double* whd_host, double* K);
+    /* the loops, one entry each, same meaning as their production counterparts above */
+    int sphx_find_neighbors_sph_f64(const SphxStepArgsF64* a, SphxStepResult* r);
+    int sphx_xmass_f64(const SphxStepArgsF64* a);
+    int sphx_ve_def_gradh_f64(const SphxStepArgsF64* a);
+    int sphx_eos_f64(const SphxStepArgsF64* a);
+    int sphx_iad_divv_curlv_f64(const SphxStepArgsF64* a, SphxStepResult* r);
+    int sphx_av_switches_f64(const SphxStepArgsF64* a);
+    int sphx_momentum_energy_f64(const SphxStepArgsF64* a, SphxStepResult* r);
+    int sphx_hydro_step_f64(const SphxStepArgsF64* a, SphxStepResult* r);
+    int sphx_export_neighbors_f64(const SphxStepArgsF64* a, unsigned* neighbors_dev);
+
     /* --- cstone call shape ------------------------------------------------------------------------------------------- */
 
     /* cstone::findNeighbors batch overload (domain/include/cstone/findneighbors.hpp:149-170): for i in [first,last)

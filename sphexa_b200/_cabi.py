@@ -42,6 +42,23 @@ class SphxStepArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspaceBytes", C.c_size_t), ("stream", C.c_void_p)]
 
 
+class SphxFieldsF64(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in FIELD_NAMES]
+
+
+class SphxParamsF64(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("K", "Kcour", "Krho", "gamma", "minDt", "polytropic_const", "polytropic_index",
+                                          "muiConst", "soundSpeedConst", "alphamin", "alphamax", "decay_constant", "Atmin",
+                                          "Atmax", "ramp")] + \
+               [("ng0", C.c_uint), ("ngmax", C.c_uint), ("eosChoice", C.c_int), ("avClean", C.c_int)]
+
+
+class SphxStepArgsF64(C.Structure):
+    _fields_ = [("f", SphxFieldsF64), ("numLocal", C.c_size_t), ("first", C.c_size_t), ("last", C.c_size_t),
+                ("p", SphxParamsF64), ("box", SphxBox), ("tree", SphxTreeView), ("wh", C.c_void_p), ("whd", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspaceBytes", C.c_size_t), ("stream", C.c_void_p)]
+
+
 class SphxStepResult(C.Structure):
     _fields_ = [("minDtCourant", C.c_double), ("minDtRho", C.c_double), ("totalNeighbors", C.c_ulong),
                 ("maxNc", C.c_uint), ("numHIterated", C.c_uint)]
@@ -129,7 +146,7 @@ EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_debug_candidate_chunk", 
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
            "sphx_powf_host", "sphx_sfc_assignment_host", "sphx_find_halos_host", "sphx_comm_unique_id",
            "sphx_comm_init", "sphx_comm_free", "sphx_halo_exchange", "sphx_allreduce_f64", "sphx_hydro_step_dist",
-           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_reduce_step_result", "sphx_comm_rank", "sphx_domain_create", "sphx_domain_destroy", "sphx_domain_sync_dist", "sphx_domain_exchange_halos", "sphx_domain_halo_plan", "sphx_domain_copy_local_keys", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
+           "sphx_allreduce_device", "sphx_exchange_slices", "sphx_reduce_step_result", "sphx_comm_rank", "sphx_domain_create", "sphx_domain_destroy", "sphx_domain_sync_dist", "sphx_domain_exchange_halos", "sphx_domain_halo_plan", "sphx_domain_copy_local_keys", "sphx_workspace_bytes_f64", "sphx_make_tables_host_f64", "sphx_find_neighbors_sph_f64", "sphx_xmass_f64", "sphx_ve_def_gradh_f64", "sphx_eos_f64", "sphx_iad_divv_curlv_f64", "sphx_av_switches_f64", "sphx_momentum_energy_f64", "sphx_hydro_step_f64", "sphx_export_neighbors_f64", "sphx_cell_plan_build_host", "sphx_cell_plan_free", "sphx_cell_plan_sizes", "sphx_cell_plan_get", "sphx_cell_plan_build_host_rings",
            "sphx_cell_plan_device_bytes", "sphx_cell_plan_build_device",
            "sphx_domain_sync_bytes", "sphx_domain_sync", "sphx_cell_histogram", "sphx_reorder_fields", "sphx_compute_timestep",
            "sphx_compute_positions", "sphx_update_smoothing_length", "sphx_integrate", "sphx_conserved_scratch_bytes",
@@ -189,6 +206,14 @@ def load():
     L.sphx_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.sphx_hydro_step_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_reduce_step_result.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.sphx_workspace_bytes_f64.restype = C.c_size_t
+    L.sphx_workspace_bytes_f64.argtypes = [C.c_size_t, C.c_uint]
+    L.sphx_make_tables_host_f64.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    for name in ("sphx_find_neighbors_sph_f64", "sphx_iad_divv_curlv_f64", "sphx_momentum_energy_f64",
+                 "sphx_hydro_step_f64", "sphx_export_neighbors_f64"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+    for name in ("sphx_xmass_f64", "sphx_ve_def_gradh_f64", "sphx_eos_f64", "sphx_av_switches_f64"):
+        getattr(L, name).argtypes = [C.c_void_p]
     L.sphx_comm_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sphx_domain_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
     L.sphx_domain_destroy.argtypes = [C.c_void_p]

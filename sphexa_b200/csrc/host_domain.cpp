@@ -209,6 +209,58 @@ struct SphxHostTree
     int                   numNodes{0}, numLeaves{0};
 };
 
+namespace
+{
+template<class T>
+int makeTables(double sincIndex, T* wh, T* whd, double* K)
+{
+    if (!wh || !whd || !K) return SPHX_ERR_INVALID;
+    const double halfPi = 1.57079632679489661923; // M_PI_2
+    const double pi     = 3.14159265358979323846;
+    auto sinc = [=](double v)
+    {
+        if (v == 0.0) return 1.0;
+        double pv = halfPi * v;
+        return std::sin(pv) / pv;
+    };
+    auto kernel = [=](double v) { return std::pow(sinc(v), sincIndex); };
+    auto kernelDerivative = [=](double v)
+    {
+        if (v == 0.0) return sincIndex * std::pow(sinc(v), sincIndex - 1) * 0.0;
+        double pv = halfPi * v;
+        double sv = std::sin(pv) / (pv);
+        double ds = sv * halfPi * ((std::cos(pv) / std::sin(pv)) - 1.0 / pv);
+        return sincIndex * std::pow(sinc(v), sincIndex - 1) * ds;
+    };
+
+    // normalisation: 1 / integral of 4 pi x^2 W(x) over [0, 2], composite Simpson with 2000 intervals where odd and
+    // even interior samples are sorted before summation (sph_kernel_tables.hpp:22-56,77-84)
+    {
+        const uint64_t      nInt = 2000;
+        const double        step = 2.0 / double(nInt);
+        auto                vol  = [&](double xx) { return 4.0 * pi * xx * xx * kernel(xx); };
+        std::vector<double> odd, even;
+        for (uint64_t i = 1; i < nInt; ++i)
+            ((i & 1) ? odd : even).push_back(vol(0.0 + double(i) * step));
+        std::sort(odd.begin(), odd.end());
+        std::sort(even.begin(), even.end());
+        double so = std::accumulate(odd.begin(), odd.end(), 0.0), se = std::accumulate(even.begin(), even.end(), 0.0);
+        *K        = 1.0 / (step / 3.0 * (vol(0.0) + vol(2.0) + 4.0 * so + 2.0 * se));
+    }
+
+    // tabulation: the abscissa is stepped and rounded in T, the functor evaluates in double
+    // (sph_kernel_tables.hpp:86-101, SURVEY App. A4)
+    const T dx = T((2.0 - 0.0) / 19999);
+    for (size_t i = 0; i < 20000; ++i)
+    {
+        T v    = T(0.0 + double(T(i) * dx));
+        wh[i]  = T(kernel(double(v)));
+        whd[i] = T(kernelDerivative(double(v)));
+    }
+    return SPHX_OK;
+}
+} // namespace
+
 extern "C"
 {
 
@@ -681,52 +733,11 @@ float sphx_powf_host(float x, float y) { return sphx::glibcPowf(x, y); }
 
 /* -------------------------------------------- kernel tables -------------------------------------------- */
 
-int sphx_make_tables_host(double sincIndex, float* wh, float* whd, double* K)
+
+int sphx_make_tables_host(double sincIndex, float* wh, float* whd, double* K) { return makeTables(sincIndex, wh, whd, K); }
+int sphx_make_tables_host_f64(double sincIndex, double* wh, double* whd, double* K)
 {
-    if (!wh || !whd || !K) return SPHX_ERR_INVALID;
-    const double halfPi = 1.57079632679489661923; // M_PI_2
-    const double pi     = 3.14159265358979323846;
-    auto sinc = [=](double v)
-    {
-        if (v == 0.0) return 1.0;
-        double pv = halfPi * v;
-        return std::sin(pv) / pv;
-    };
-    auto kernel = [=](double v) { return std::pow(sinc(v), sincIndex); };
-    auto kernelDerivative = [=](double v)
-    {
-        if (v == 0.0) return sincIndex * std::pow(sinc(v), sincIndex - 1) * 0.0;
-        double pv = halfPi * v;
-        double sv = std::sin(pv) / (pv);
-        double ds = sv * halfPi * ((std::cos(pv) / std::sin(pv)) - 1.0 / pv);
-        return sincIndex * std::pow(sinc(v), sincIndex - 1) * ds;
-    };
-
-    // normalisation: 1 / integral of 4 pi x^2 W(x) over [0, 2], composite Simpson with 2000 intervals where odd and
-    // even interior samples are sorted before summation (sph_kernel_tables.hpp:22-56,77-84)
-    {
-        const uint64_t      nInt = 2000;
-        const double        step = 2.0 / double(nInt);
-        auto                vol  = [&](double xx) { return 4.0 * pi * xx * xx * kernel(xx); };
-        std::vector<double> odd, even;
-        for (uint64_t i = 1; i < nInt; ++i)
-            ((i & 1) ? odd : even).push_back(vol(0.0 + double(i) * step));
-        std::sort(odd.begin(), odd.end());
-        std::sort(even.begin(), even.end());
-        double so = std::accumulate(odd.begin(), odd.end(), 0.0), se = std::accumulate(even.begin(), even.end(), 0.0);
-        *K        = 1.0 / (step / 3.0 * (vol(0.0) + vol(2.0) + 4.0 * so + 2.0 * se));
-    }
-
-    // tabulation: the abscissa is stepped and rounded in float, the functor evaluates in double
-    // (sph_kernel_tables.hpp:86-101, SURVEY App. A4)
-    const float dx = float((2.0 - 0.0) / 19999);
-    for (size_t i = 0; i < 20000; ++i)
-    {
-        float v = float(0.0 + double(float(i) * dx));
-        wh[i]   = float(kernel(double(v)));
-        whd[i]  = float(kernelDerivative(double(v)));
-    }
-    return SPHX_OK;
+    return makeTables(sincIndex, wh, whd, K);
 }
 
 } // extern "C"

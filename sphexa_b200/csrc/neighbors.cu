@@ -30,20 +30,32 @@ struct WarpShared
     double sx[kLeafBatch], sy[kLeafBatch], sz[kLeafBatch];
 };
 
+//! Th: type of the smoothing lengths (float in the production type set, double in the all-double one)
+template<class Th>
 struct Target
 {
     double x, y, z;   // position
-    float  h;         // smoothing length
-    float  radiusSq;  // Th(4) * h * h   (findneighbors.hpp:93)
-    float  cellRadSq; // radiusSq * searchExtFactor^2 (findneighbors.hpp:94)
+    Th     h;         // smoothing length
+    Th     radiusSq;  // Th(4) * h * h   (findneighbors.hpp:93)
+    Th     cellRadSq; // radiusSq * searchExtFactor^2 (findneighbors.hpp:94)
     bool   usePbc;    // anyPbc && !insideBox(particle, 2h) (findneighbors.hpp:98-100)
     bool   valid;
 };
 
-__device__ __forceinline__ void setupTarget(Target& t, const DevBox& box, float searchExt)
+__device__ __forceinline__ float  mulRn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mulRn(double a, double b) { return __dmul_rn(a, b); }
+
+//! sph::updateH (kernels.hpp:26-32) for T = double (the float version emulates glibc's powf bit for bit)
+__device__ __forceinline__ double updateH(unsigned ng0, unsigned nc, double h)
 {
-    t.radiusSq  = __fmul_rn(__fmul_rn(4.0f, t.h), t.h);
-    t.cellRadSq = __fmul_rn(__fmul_rn(t.radiusSq, searchExt), searchExt);
+    return h * 0.5 * pow(1.0 + 1023.0 * double(ng0) / double(nc), 1.0 / 10.0);
+}
+
+template<class Th>
+__device__ __forceinline__ void setupTarget(Target<Th>& t, const DevBox& box, float searchExt)
+{
+    t.radiusSq  = mulRn(mulRn(Th(4), t.h), t.h);
+    t.cellRadSq = mulRn(mulRn(t.radiusSq, Th(searchExt)), Th(searchExt));
     double ext  = __dmul_rn(2.0, double(t.h));
     bool inside = __dsub_rn(t.x, ext) >= box.xmin && __dsub_rn(t.y, ext) >= box.ymin &&
                   __dsub_rn(t.z, ext) >= box.zmin && __dadd_rn(t.x, ext) <= box.xmax &&
@@ -56,7 +68,8 @@ __device__ __forceinline__ void setupTarget(Target& t, const DevBox& box, float 
  * @param record   lanes that (re)build their list in this pass; the others only take part in the cooperative work
  * @return         per-lane neighbour count (self excluded, not capped) for recording lanes
  */
-__device__ unsigned traverseWarp(const Target& t, unsigned iSelf, bool record, const DevBox& box,
+template<class Th>
+__device__ unsigned traverseWarp(const Target<Th>& t, unsigned iSelf, bool record, const DevBox& box,
                                  const SphxTreeView& tree, const double* __restrict__ x, const double* __restrict__ y,
                                  const double* __restrict__ z, unsigned ngmax, unsigned* __restrict__ listCol,
                                  WarpShared& sm, unsigned* errFlags)
@@ -214,7 +227,8 @@ __device__ unsigned traverseWarp(const Target& t, unsigned iSelf, bool record, c
 }
 
 /*! @brief search + h-iteration for one warp; returns nc = 1 + count for valid lanes */
-__device__ unsigned searchWithHIteration(Target& t, unsigned i, const DevBox& box, const SphxTreeView& tree,
+template<class Th>
+__device__ unsigned searchWithHIteration(Target<Th>& t, unsigned i, const DevBox& box, const SphxTreeView& tree,
                                          const double* x, const double* y, const double* z, unsigned ng0,
                                          unsigned ngmax, unsigned* listCol, WarpShared& sm, StepScalars* scal,
                                          bool iterateH, bool& hChanged)
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 
     WarpShared& sm = shared[warpInBlock];
     unsigned    i  = first + unsigned(group) * kGroupSize + lane;
-    Target      t;
+    Target<float> t;
     t.valid     = i < last;
     unsigned il = t.valid ? i : last - 1;
     t.x = x[il], t.y = y[il], t.z = z[il], t.h = h[il];
@@ -271,6 +285,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     bool      hChanged;
     unsigned  ncSph = searchWithHIteration(t, i, box, tree, x, y, z, 0, ngmax, listCol, sm, scal, false, hChanged);
     if (t.valid) { counts[i - first] = ncSph - 1; }
+}
+
+/*! @brief sph::findNeighborsSph (sph/find_neighbors.hpp:11-44) for the all-double type set: search with the coupled
+ *  h-iteration, writes h, nc = 1 + count and the lane-interleaved particle-index list */
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    findNeighborsSphF64Kernel(unsigned first, unsigned last, DevBox box, SphxTreeView tree,
+                              const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                              double* __restrict__ h, unsigned ng0, unsigned ngmax, unsigned* __restrict__ list,
+                              unsigned* __restrict__ nc, StepScalars* scal)
+{
+    __shared__ WarpShared shared[kWarpsPerBlock];
+    const unsigned        warpInBlock = threadIdx.x >> 5;
+    const unsigned        lane        = laneId();
+    const size_t          group       = size_t(blockIdx.x) * kWarpsPerBlock + warpInBlock;
+    const size_t          numGroups   = (size_t(last - first) + kGroupSize - 1) / kGroupSize;
+    if (group >= numGroups) { return; }
+
+    WarpShared&    sm = shared[warpInBlock];
+    unsigned       i  = first + unsigned(group) * kGroupSize + lane;
+    Target<double> t;
+    t.valid     = i < last;
+    unsigned il = t.valid ? i : last - 1;
+    t.x = x[il], t.y = y[il], t.z = z[il], t.h = h[il];
+
+    unsigned* listCol = list + nbListIndex(group, ngmax, 0, lane);
+    bool      hChanged;
+    unsigned  ncSph = searchWithHIteration(t, i, box, tree, x, y, z, ng0, ngmax, listCol, sm, scal, true, hChanged);
+    if (t.valid)
+    {
+        nc[i] = ncSph;
+        if (hChanged) { h[i] = t.h; }
+    }
+    unsigned long long sum = t.valid ? ncSph : 0;
+    unsigned           mx  = t.valid ? ncSph : 0, it = (t.valid && hChanged) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        sum += __shfl_xor_sync(kFullMask, sum, o);
+        mx = max(mx, __shfl_xor_sync(kFullMask, mx, o));
+        it += __shfl_xor_sync(kFullMask, it, o);
+    }
+    if (lane == 0)
+    {
+        atomicAdd(&scal->totalNeighbors, sum);
+        atomicMax(&scal->maxNc, mx);
+        if (it) { atomicAdd(&scal->numHIterated, it); }
+    }
 }
 
 //! lane-interleaved ELL -> reference CPU layout neighbors[(i-first)*ngmax + k]
@@ -314,6 +374,18 @@ void launchFindNeighbors(const double* x, const double* y, const double* z, cons
     unsigned blocks    = (numGroups + kWarpsPerBlock - 1) / kWarpsPerBlock;
     findNeighborsKernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(first, last, makeDevBox(box), tree, x, y, z, h,
                                                                    ngmax, list, counts, scal);
+}
+
+void launchFindNeighborsSphF64(const double* x, const double* y, const double* z, double* h, unsigned first, unsigned last,
+                               const SphxBox& box, const SphxTreeView& tree, unsigned ng0, unsigned ngmax,
+                               unsigned* list, unsigned* nc, StepScalars* scal, cudaStream_t stream)
+{
+    unsigned n = last - first;
+    if (n == 0) return;
+    unsigned numGroups = (n + kGroupSize - 1) / kGroupSize;
+    unsigned blocks    = (numGroups + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    findNeighborsSphF64Kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(first, last, makeDevBox(box), tree, x, y, z,
+                                                                         h, ng0, ngmax, list, nc, scal);
 }
 
 void launchExportNeighbors(unsigned numAssigned, unsigned ngmax, const unsigned* list, const unsigned* counts,

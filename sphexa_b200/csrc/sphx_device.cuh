@@ -176,6 +176,13 @@ struct StepScalars
     unsigned           work[8];  // dynamic work counters of the persistent loop kernels
 };
 
+//! the min / max reductions of the all-double path (loops_f64.cu)
+struct StepScalarsF64
+{
+    double minDtCourant;
+    double maxDivv;
+};
+
 constexpr unsigned kErrHConv     = 1u;
 constexpr unsigned kErrNgmax     = 2u;
 constexpr unsigned kErrTraversal = 4u;

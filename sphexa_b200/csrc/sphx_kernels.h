@@ -26,6 +26,10 @@ void launchFindNeighbors(const double* x, const double* y, const double* z, cons
                          unsigned* counts, StepScalars* scal, cudaStream_t stream);
 void launchExportNeighbors(unsigned numAssigned, unsigned ngmax, const unsigned* list, const unsigned* counts,
                            bool countsIncludeSelf, unsigned* out, cudaStream_t stream);
+// the same search with the coupled h-iteration for the all-double type set (loops_f64.cu)
+void launchFindNeighborsSphF64(const double* x, const double* y, const double* z, double* h, unsigned first, unsigned last,
+                               const SphxBox& box, const SphxTreeView& tree, unsigned ng0, unsigned ngmax,
+                               unsigned* list, unsigned* nc, StepScalars* scal, cudaStream_t stream);
 
 // block search of the hydro step (search.cu)
 cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t stream);

@@ -243,6 +243,94 @@ class HydroData:
         return self.export_neighbors_device().cpu().numpy().view(np.uint32)
 
 
+class HydroDataF64:
+    """The all-double type set (every field fp64) behind sphx_*_f64: the precision path of libsphx (csrc/loops_f64.cu),
+    one rank. Same call order as HydroData; fields are torch float64 tensors."""
+
+    def __init__(self, n: int, box_lim, boundary, params: Params, device="cuda:0"):
+        self.L = _cabi.load()
+        _cabi.check(self.L.sphx_device_check())
+        self.device = torch.device(device)
+        self.n, self.first, self.last = n, 0, n
+        self.box_lim, self.boundary = [float(v) for v in box_lim], [int(b) for b in boundary]
+        self.p = params
+        self.f: dict[str, torch.Tensor] = {}
+        for name in _cabi.FIELD_NAMES:
+            if name in ("u", "rho", "p") or (name.startswith("dV") and not params.avClean):
+                continue
+            self.f[name] = torch.zeros(n, dtype=torch.int32 if name == "nc" else torch.float64, device=self.device)
+        wh, whd, K = np.zeros(20000), np.zeros(20000), C.c_double(0)
+        _cabi.check(self.L.sphx_make_tables_host_f64(6.0, wh.ctypes.data, whd.ctypes.data, C.byref(K)))
+        if self.p.K == 0.0:
+            self.p.K = K.value
+        self.wh, self.whd = torch.from_numpy(wh).to(self.device), torch.from_numpy(whd).to(self.device)
+        self.tree: DeviceTree | None = None
+        self.workspace = torch.empty(self.L.sphx_workspace_bytes_f64(n, self.p.ngmax), dtype=torch.uint8,
+                                     device=self.device)
+        self.result = _cabi.SphxStepResult()
+
+    def set_fields(self, **arrays):
+        for k, a in arrays.items():
+            self.f[k].copy_(torch.from_numpy(np.ascontiguousarray(a, np.float64)))
+
+    def get(self, name) -> np.ndarray:
+        a = self.f[name].cpu().numpy()
+        return a.view(np.uint32) if name == "nc" else a
+
+    def set_tree(self, t):
+        self.tree = t if isinstance(t, DeviceTree) else DeviceTree(t, self.device)
+
+    def args(self) -> _cabi.SphxStepArgsF64:
+        a = _cabi.SphxStepArgsF64()
+        for name in _cabi.FIELD_NAMES:
+            setattr(a.f, name, self.f[name].data_ptr() if name in self.f else None)
+        a.numLocal, a.first, a.last = self.n, self.first, self.last
+        for name, _ in _cabi.SphxParamsF64._fields_:
+            setattr(a.p, name, getattr(self.p, name))
+        a.box = host.make_box(self.box_lim, self.boundary)
+        a.tree = self.tree.view()
+        a.wh, a.whd = self.wh.data_ptr(), self.whd.data_ptr()
+        a.workspace, a.workspaceBytes = self.workspace.data_ptr(), self.workspace.numel()
+        return a
+
+    def _call(self, name, with_result=False):
+        a = self.args()
+        fn = getattr(self.L, name)
+        _cabi.check(fn(C.byref(a), C.byref(self.result)) if with_result else fn(C.byref(a)))
+
+    def find_neighbors_sph(self):
+        self._call("sphx_find_neighbors_sph_f64", True)
+
+    def xmass(self):
+        self._call("sphx_xmass_f64")
+
+    def ve_def_gradh(self):
+        self._call("sphx_ve_def_gradh_f64")
+
+    def eos(self):
+        self._call("sphx_eos_f64")
+
+    def iad_divv_curlv(self):
+        self._call("sphx_iad_divv_curlv_f64", True)
+
+    def av_switches(self):
+        self._call("sphx_av_switches_f64")
+
+    def momentum_energy(self):
+        self._call("sphx_momentum_energy_f64", True)
+
+    def hydro_step(self):
+        self._call("sphx_hydro_step_f64", True)
+        return self.result
+
+    def export_neighbors(self) -> np.ndarray:
+        out = torch.zeros(self.n * self.p.ngmax, dtype=torch.int32, device=self.device)
+        a = self.args()
+        _cabi.check(self.L.sphx_export_neighbors_f64(C.byref(a), C.c_void_p(out.data_ptr())))
+        torch.cuda.synchronize(self.device)
+        return out.cpu().numpy().view(np.uint32)
+
+
 class Turbulence:
     """sph::TurbulenceData + sph::driveTurbulence (sph/include/sph/hydro_turb/turbulence_data.hpp, driver.hpp:102-128)
     behind sphx_turbulence_* / sphx_drive_turbulence: host state (modes, OU phases, std::mt19937) and device tables

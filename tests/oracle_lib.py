@@ -156,7 +156,7 @@ def hydro_step_f(d: dict, wh=None, whd=None) -> dict:
                 dts=np.array([dtCour.value, dtRho.value]), fails=fails, wh=wh, whd=whd, K=prm.K)
 
 
-def momentum_fields_d(d: dict) -> dict:
+def momentum_fields_d(d: dict, double_table: bool = False) -> dict:
     """ax, ay, az, du of a reference dump re-evaluated with EVERY operation in fp64 (the all-double instantiation of
     momentum_energy_kern.hpp:65-222) from the dump's own inputs of that loop (h, nc, neighbours, prho, c, c11..c33, kx,
     xm, alpha as the reference stored them, widened to double). |dump - this| is the reference's own fp32 rounding and
@@ -166,9 +166,12 @@ def momentum_fields_d(d: dict) -> dict:
     ngmax = int(d["ngmax"][0])
     v = d["params"]
     box = make_box(d["box"], d["boundary"])
-    wh, _, _ = tables_d()
-    # the production table is float: use ITS values (widened), so that only the arithmetic differs, not the inputs
-    wh = d["wh"].astype(np.float64) if "wh" in d else tables_f()[0].astype(np.float64)
+    # the production table is float: by default use ITS values (widened), so that only the arithmetic differs, not the
+    # inputs; double_table: the table of the all-double instantiation (createWharmonicTable<double>)
+    if double_table:
+        wh, _, _ = tables_d()
+    else:
+        wh = d["wh"].astype(np.float64) if "wh" in d else tables_f()[0].astype(np.float64)
     dd = {k: np.ascontiguousarray(d[k], np.float64) for k in ("x", "y", "z", "vx", "vy", "vz", "h", "m", "prho", "c", "c11",
                                                              "c12", "c13", "c22", "c23", "c33", "kx", "xm", "alpha")}
     nb = np.ascontiguousarray(d["neighbors"], np.uint32)
