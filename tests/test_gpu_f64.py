@@ -149,5 +149,5 @@ def test_all_double_step_is_the_yardstick_of_the_production_path(sx, oracle, fna
     prod = sx.sim.from_dump(d)
     prod.hydro_step()
     np.testing.assert_array_equal(hd.get("nc"), prod.get("nc"))
-    np.testing.assert_allclose(hd.get("h"), prod.get("h"), rtol=2e-7)
+    np.testing.assert_allclose(hd.get("h"), prod.get("h"), rtol=1e-6)  # up to 10 float roundings of the h-iteration
     assert_fields_close({k: prod.get(k) for k in F32_FIELDS}, {k: hd.get(k) for k in F32_FIELDS})
