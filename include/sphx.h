@@ -20,6 +20,9 @@
  *    failures (xmass_gpu.cu:127-128) and exits on CUDA errors (cstone/cuda/errorcheck.cuh:14-26); the C++ wrappers turn the
  *    status codes back into those behaviours.
  *  - all work is enqueued on `stream`; functions that return host-visible scalars synchronise that stream.
+ *  - threads and devices: a call works on the CURRENT CUDA device of the calling thread; one process may drive several
+ *    devices from one thread each (launch parameters are cached per device, nothing device-dependent is process-wide).
+ *    Calls for the same workspace / domain object must not overlap.
  *  - there is no CPU fallback: without a CUDA device every compute entry point returns SPHX_ERR_NO_DEVICE.
  */
 #ifndef SPHX_H

@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,11 +44,9 @@ struct NcclApi
 template<class Err>
 NcclApi* ncclApi(Err& err)
 {
-    static NcclApi api;
-    static bool    tried = false;
-    if (!tried)
-    {
-        tried = true;
+    static NcclApi        api;
+    static std::once_flag once;
+    std::call_once(once, [] {
         // RTLD_NOLOAD first: reuse the copy the host application (e.g. torch) already loaded
         void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -70,7 +69,7 @@ NcclApi* ncclApi(Err& err)
 #undef SPHX_SYM
             if (ok) api.handle = h;
         }
-    }
+    });
     if (!api.handle)
     {
         err = "libnccl.so.2 not found or incomplete";

@@ -1011,40 +1011,33 @@ __global__ void exportBlockNeighborsKernel(unsigned numAssigned, unsigned ngmax,
 template<class C>
 static cudaError_t configureSearch()
 {
-    static bool      configured = false;
-    constexpr size_t bytes      = searchSharedBytes<C>();
+    static std::atomic<bool> configured[64]; // per device
+    constexpr size_t         bytes = searchSharedBytes<C>();
     static_assert(bytes <= 227 * 1024, "search kernel shared memory exceeds the 227 KB CTA limit");
-    if (bytes <= 48 * 1024 || configured) return cudaSuccess;
+    const int dev = DeviceCache::device();
+    if (bytes <= 48 * 1024 || configured[dev].load(std::memory_order_acquire)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(blockSearchKernel<true, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(bytes));
-    if (e == cudaSuccess) configured = true;
+    if (e == cudaSuccess) configured[dev].store(true, std::memory_order_release);
     return e;
 }
 
-static int smCountSearch()
-{
-    static int n = 0;
-    if (n == 0)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int smCountSearch() { return DeviceCache::smCount(); }
 
-//! resident CTAs per SM of the search kernel (occupancy query, cached)
+//! resident CTAs per SM of the search kernel (occupancy query, cached per device)
 static int searchCtasPerSm()
 {
-    static int n = 0;
-    if (n == 0)
+    static std::atomic<int> n[64];
+    const int               dev = DeviceCache::device();
+    int                     v   = n[dev].load(std::memory_order_relaxed);
+    if (v == 0)
     {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, blockSearchKernel<true, CapsStd>, kSearchThreads,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, blockSearchKernel<true, CapsStd>, kSearchThreads,
                                                       searchSharedBytes<CapsStd>());
-        if (n <= 0) n = 1;
+        if (v <= 0) v = 1;
+        n[dev].store(v, std::memory_order_relaxed);
     }
-    return n;
+    return v;
 }
 
 cudaError_t launchBlockSearch(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t stream)

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <string>
 
@@ -43,6 +44,33 @@ cudaError_t launchIadDivvCurlv(const SphxStepArgs& a, const WorkspaceLayout& w, 
 cudaError_t launchAvSwitches(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchMomentumEnergy(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 void        setCandidateChunkLimit(unsigned n);
+
+/*! per-device caches of launch parameters: one process may drive several GPUs (one thread per GPU), so nothing that
+ *  depends on the device is kept in a plain static. Slot = current device (0 .. 63); values are written with relaxed
+ *  atomics, every writer stores the same value. */
+struct DeviceCache
+{
+    static int device()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return dev < 0 || dev >= 64 ? 0 : dev;
+    }
+    //! number of SMs of the current device
+    static int smCount()
+    {
+        static std::atomic<int> n[64];
+        const int               dev = device();
+        int                     v   = n[dev].load(std::memory_order_relaxed);
+        if (v == 0)
+        {
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+            if (v <= 0) v = 148;
+            n[dev].store(v, std::memory_order_relaxed);
+        }
+        return v;
+    }
+};
 
 // Hilbert state machine tables for the device (host_domain.cpp)
 int hilbertTablesFlat(uint8_t* digit, uint8_t* next, uint8_t* octant, int maxStates);

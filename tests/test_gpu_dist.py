@@ -15,6 +15,18 @@ OUT = ["h", "nc", "xm", "kx", "gradh", "prho", "c", "c11", "c12", "c13", "c22", 
 
 def _case(name, side):
     from sphexa_b200 import cases
+    if name == "onecell":
+        # smoothing lengths so large that the decomposition works on ONE cell (level 0): with two ranks one of them owns
+        # every particle and the other none (more ranks than occupied cells)
+        from sphexa_b200.sim import Params
+        rng = np.random.default_rng(3)
+        n = side ** 3
+        pts = rng.random((3, n)) - 0.5
+        p = Params(minDt=1e-4, minDt_m1=1e-4, ng0=60, ngmax=150)
+        f = dict(h=np.float32(0.13), m=np.float32(1.0 / n), temp=np.float64(1.0), alpha=np.float32(0.05),
+                 vx=np.zeros(n, np.float32), vy=np.zeros(n, np.float32), vz=np.zeros(n, np.float32))
+        return dict(x=pts[0].copy(), y=pts[1].copy(), z=pts[2].copy(), fields=f, params=p, box=[-0.5, 0.5] * 3,
+                    boundary=[1, 1, 1])
     if name == "turbstir":  # turbulence box at rest: all motion comes from the stirring (turbulence-ve propagator)
         g = cases.turbulence_global(side)
         for k in ("vx", "vy", "vz"):
@@ -196,6 +208,23 @@ def test_multi_gpu_loop_equals_single_gpu(world, name, side, steps):
     assert (st[:, :, 2] > st[:, :, 1]).all()                          # halos are really there
     imbalance = st[:, :, 1].max(0) / st[:, :, 1].mean(0)
     assert imbalance.max() < 1.3
+
+
+def test_more_ranks_than_occupied_cells():
+    """a rank may end up with NO particles (here: the plan has a single cell): the sync, the distributed hydro step, the
+    reductions and integrate go through on the empty rank and the loop equals the one-rank loop"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ref, ref_res = _run_sim(1, "onecell", 10, 3)
+    got, res = _run_sim(2, "onecell", 10, 3)
+    st = np.stack([res[r]["stats"] for r in range(2)])       # [rank, step, (first, nAssigned, nLocal, level)]
+    assert (st[:, :, 3] == 0).all() and (st[:, :, 1].min(0) == 0).all() and (st[:, :, 1].max(0) == 1000).all()
+    np.testing.assert_array_equal(got["nc"], ref["nc"])
+    np.testing.assert_array_equal(res[0]["rows"][:, 8], ref_res[0]["rows"][:, 8])
+    np.testing.assert_allclose(res[0]["rows"][:, 2:6], ref_res[0]["rows"][:, 2:6], rtol=1e-6)
+    for k in ("x", "y", "z", "h"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-6, atol=1e-9)
 
 
 @pytest.mark.parametrize("world", [1, 2])
