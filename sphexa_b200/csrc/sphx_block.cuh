@@ -40,6 +40,8 @@ constexpr int      kSearchWork     = 5;   // StepScalars::work slot of the block
 
 constexpr unsigned kBlockFold = 1u; // BlockDesc::flags: fold mode
 
+constexpr int kPolyDeg = 13; // degree (in s = v^2 / 2 - 1) of the polynomials that stand for the kernel tables
+
 struct BlockDesc
 {
     double   ox, oy, oz; // block origin (centre of the bounding box of the targets' search spheres)
@@ -97,6 +99,11 @@ struct LoopArgs
     const float4*    cand;
     const float*     wh;
     const float*     whd;
+    // kernel tables as polynomials (loops.cu: fitKernelPoly), used by the <Poly = true> instantiations:
+    // wh(v) = sum_k pw[k] s^k, whd(v) = v sum_k pd[k] s^k with s = v^2 / 2 - 1; both halves of an entry hold the same
+    // coefficient, so that it can be the operand of a packed f32x2 FMA straight from the constant bank
+    float2           pw[kPolyDeg + 1];
+    float2           pd[kPolyDeg + 1];
     StepScalars*     scal;
     double           K, minDt;
     float            Kcour, alphamin, alphamax, decay_constant, Atmin, Atmax, ramp;
