@@ -48,7 +48,9 @@ extern "C"
         SPHX_ERR_H_CONVERGENCE  = 5, /* coupled h / neighbour-count iteration did not converge (xmass_gpu.cu:128) */
         SPHX_ERR_NGMAX_OVERFLOW = 6, /* a particle kept more than ngmax neighbours after the h-iteration */
         SPHX_ERR_TRAVERSAL      = 7, /* traversal stack exhausted (xmass_gpu.cu:127) */
-        SPHX_ERR_NCCL           = 8
+        SPHX_ERR_NCCL           = 8,
+        SPHX_ERR_TABLE          = 9 /* wh / whd were rewritten under the addresses a loop has already used (see
+                                       sphx_invalidate_tables) */
     };
 
     /* cstone::Box<double> (domain/include/cstone/sfc/box.hpp:94-174). boundary: 0 open, 1 periodic, 2 fixed */
@@ -201,6 +203,20 @@ extern "C"
     /* host: kernel tables and normalisation constant, sinc^n kernel
      * (ParticlesData::createTables particles_data.hpp:380-387; sph_kernel_tables.hpp:77-101,144-172) */
     int sphx_make_tables_host(double sincIndex, float* wh_host, float* whd_host, double* K);
+
+    /* How the loops evaluate the kernel tables (lt::lookup, sph/include/sph/table_lookup.hpp:13-26). The first loop
+     * that sees a (device, wh, whd) address pair copies both tables to the host once (synchronising the stream) and
+     * fits one polynomial in v^2 to each. If the polynomials reproduce all 20000 entries to 1e-6 of the table maximum
+     * (the sinc^n kernels up to n ~ 7 do; lt::lookup's own fp32 rounding noise is 1e-7), the loops evaluate them
+     * instead of the tables: no shared-memory table, no dependent random reads. Otherwise the loops interpolate copies
+     * of the tables in shared memory exactly as the reference does. The fit is kept per address pair: a caller that
+     * REWRITES a table in place must call sphx_invalidate_tables(); every loop launch spot-checks ~2000 entries and the
+     * step fails with SPHX_ERR_TABLE if they no longer match. Setting the environment variable SPHX_FORCE_TABLE
+     * selects the shared-memory tables for every table pair first seen afterwards (A/B measurements, tests). */
+    void sphx_invalidate_tables(void);
+    /* 1: polynomial evaluation, 0: shared-memory tables for this pair; < 0: -(error code). errW / errD (optional):
+     * largest deviation of the fit from a table entry, relative to the table maximum */
+    int sphx_table_mode(const float* wh, const float* whd, void* stream, double* errW, double* errD);
 
     /* --- the hot path ---------------------------------------------------------------------------------------------- */
 

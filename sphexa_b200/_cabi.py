@@ -136,11 +136,11 @@ SPHX_SYNC_PRESORTED, SPHX_SYNC_NO_TREE, SPHX_SYNC_LIMIT_SHRINK = 1, 2, 4
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int))
 
 STATUS = {0: "SPHX_OK", 1: "SPHX_ERR_NO_DEVICE", 2: "SPHX_ERR_CUDA", 3: "SPHX_ERR_INVALID", 4: "SPHX_ERR_WORKSPACE",
-          5: "SPHX_ERR_H_CONVERGENCE", 6: "SPHX_ERR_NGMAX_OVERFLOW", 7: "SPHX_ERR_TRAVERSAL", 8: "SPHX_ERR_NCCL"}
+          5: "SPHX_ERR_H_CONVERGENCE", 6: "SPHX_ERR_NGMAX_OVERFLOW", 7: "SPHX_ERR_TRAVERSAL", 8: "SPHX_ERR_NCCL", 9: "SPHX_ERR_TABLE"}
 
 # every symbol include/sphx.h declares
 EXPORTS = ["sphx_last_error", "sphx_abi_version", "sphx_debug_candidate_chunk", "sphx_device_check", "sphx_workspace_bytes", "sphx_workspace_layout",
-           "sphx_make_tables_host", "sphx_find_neighbors_xmass", "sphx_find_neighbors_sph", "sphx_xmass", "sphx_ve_def_gradh", "sphx_eos",
+           "sphx_make_tables_host", "sphx_invalidate_tables", "sphx_table_mode", "sphx_find_neighbors_xmass", "sphx_find_neighbors_sph", "sphx_xmass", "sphx_ve_def_gradh", "sphx_eos",
            "sphx_iad_divv_curlv", "sphx_av_switches", "sphx_momentum_energy", "sphx_hydro_step",
            "sphx_find_neighbors", "sphx_export_neighbors", "sphx_host_tree_build", "sphx_host_tree_free",
            "sphx_host_tree_sizes", "sphx_host_tree_get", "sphx_hilbert_keys_host", "sphx_update_h_host",
@@ -175,6 +175,10 @@ def load():
     L.sphx_last_error.restype = C.c_char_p
     L.sphx_workspace_bytes.restype = C.c_size_t
     L.sphx_workspace_bytes.argtypes = [C.c_size_t, C.c_uint]
+    L.sphx_invalidate_tables.restype = None
+    L.sphx_invalidate_tables.argtypes = []
+    L.sphx_table_mode.restype = C.c_int
+    L.sphx_table_mode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sphx_workspace_layout.restype = None
     L.sphx_workspace_layout.argtypes = [C.c_size_t, C.c_uint, C.c_void_p]
     L.sphx_host_tree_build.restype = C.c_void_p

@@ -90,6 +90,9 @@ int errFlagsToStatus(unsigned flags)
         return fail(SPHX_ERR_TRAVERSAL, "GPU traversal stack exhausted in neighbor search");
     if (flags & sphx::kErrHConv) return fail(SPHX_ERR_H_CONVERGENCE, "coupled nc/h-updated failed to converge");
     if (flags & sphx::kErrNgmax) return fail(SPHX_ERR_NGMAX_OVERFLOW, "neighbour count exceeds ngmax after h-iteration");
+    if (flags & sphx::kErrTable)
+        return fail(SPHX_ERR_TABLE, "the kernel tables wh / whd changed under the addresses the loops fitted their "
+                                    "polynomials to: call sphx_invalidate_tables() after rewriting a table");
     if (flags & sphx::kErrCandSpace)
         return fail(SPHX_ERR_WORKSPACE, "candidate array of the workspace exhausted (more than 16 candidates per particle)");
     return SPHX_OK;
@@ -134,6 +137,15 @@ int sphx_device_check(void)
 size_t sphx_workspace_bytes(size_t numAssigned, unsigned ngmax)
 {
     return sphx::WorkspaceLayout(numAssigned, ngmax).total;
+}
+
+void sphx_invalidate_tables(void) { sphx::invalidateKernelPolys(); }
+
+int sphx_table_mode(const float* wh, const float* whd, void* stream, double* errW, double* errD)
+{
+    if (int rc = sphx_device_check()) return -rc;
+    if (!wh || !whd) return -fail(SPHX_ERR_INVALID, "null table");
+    return sphx::kernelPolyStatus(wh, whd, static_cast<cudaStream_t>(stream), errW, errD);
 }
 
 void sphx_workspace_layout(size_t numAssigned, unsigned ngmax, size_t out[8])

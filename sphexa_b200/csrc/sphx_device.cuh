@@ -187,6 +187,7 @@ constexpr unsigned kErrHConv     = 1u;
 constexpr unsigned kErrNgmax     = 2u;
 constexpr unsigned kErrTraversal = 4u;
 constexpr unsigned kErrCandSpace = 8u;
+constexpr unsigned kErrTable     = 16u; // the kernel tables are not the ones the loops' polynomials were fitted to
 
 constexpr size_t kScalarsBytes = 256; // StepScalars + padding, keeps the list 256-byte aligned
 

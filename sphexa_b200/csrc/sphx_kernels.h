@@ -44,6 +44,9 @@ cudaError_t launchIadDivvCurlv(const SphxStepArgs& a, const WorkspaceLayout& w, 
 cudaError_t launchAvSwitches(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 cudaError_t launchMomentumEnergy(const SphxStepArgs& a, const WorkspaceLayout& w, cudaStream_t s);
 void        setCandidateChunkLimit(unsigned n);
+void        invalidateKernelPolys();
+//! 1 if the loops evaluate the tables at (wh, whd) through their polynomial fits, 0 if through shared-memory tables
+int         kernelPolyStatus(const float* wh, const float* whd, cudaStream_t s, double* errW, double* errD);
 
 /*! per-device caches of launch parameters: one process may drive several GPUs (one thread per GPU), so nothing that
  *  depends on the device is kept in a plain static. Slot = current device (0 .. 63); values are written with relaxed
