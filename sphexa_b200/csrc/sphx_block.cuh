@@ -100,7 +100,7 @@ struct LoopArgs
     const float*     wh;
     const float*     whd;
     // kernel tables as polynomials (loops.cu: fitKernelPoly), used by the <Poly = true> instantiations:
-    // wh(v) = sum_k pw[k] s^k, whd(v) = v sum_k pd[k] s^k with s = v^2 / 2 - 1; both halves of an entry hold the same
+    // wh(v) = sum_k pw[k] s^k, v whd(v) = sum_k pd[k] s^k with s = v^2 / 2 - 1; both halves of an entry hold the same
     // coefficient, so that it can be the operand of a packed f32x2 FMA straight from the constant bank
     float2           pw[kPolyDeg + 1];
     float2           pd[kPolyDeg + 1];
