@@ -102,7 +102,9 @@ void fillResult(const sphx::StepScalars& h, const SphxParams& p, SphxStepResult*
 {
     if (!r) return;
     r->minDtCourant   = double(h.minDtCourant);
-    r->minDtRho       = p.Krho / std::fabs(double(h.maxDivv)); // ts_global.hpp:94 (double / float)
+    // ts_global.hpp:94 (double / float). A rank without particles has no divergence to report: its max divv is still the
+    // identity of the reduction (-inf), and Krho / |-inf| = 0 would win the MIN over the ranks as a zero time step
+    r->minDtRho = h.maxDivv == -INFINITY ? double(INFINITY) : p.Krho / std::fabs(double(h.maxDivv));
     r->totalNeighbors = h.totalNeighbors;
     r->maxNc          = h.maxNc;
     r->numHIterated   = h.numHIterated;

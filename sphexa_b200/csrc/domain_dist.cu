@@ -262,8 +262,8 @@ const SphxHaloPlan* sphx_domain_halo_plan(const SphxDomain* d) { return d ? &d->
 
 int sphx_domain_copy_local_keys(const SphxDomain* d, uint64_t* dst, void* stream)
 {
-    if (!d || !dst) return domFail(SPHX_ERR_INVALID, "sphx_domain_copy_local_keys: null argument");
-    if (d->numLocal)
+    if (!d || (!dst && d->numLocal)) return domFail(SPHX_ERR_INVALID, "sphx_domain_copy_local_keys: null argument");
+    if (d->numLocal) // (a rank without particles: nothing to copy, dst may be null)
         DOM_CUDA(cudaMemcpyAsync(dst, d->localKeys.p, d->numLocal * 8, cudaMemcpyDeviceToDevice,
                                  static_cast<cudaStream_t>(stream)));
     return SPHX_OK;

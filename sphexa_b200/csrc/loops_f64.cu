@@ -447,7 +447,7 @@ int readResult(const SphxStepArgsF64* a, const F64Layout& lay, SphxStepResult* r
         cudaStreamSynchronize(s) != cudaSuccess)
         return f64Fail(SPHX_ERR_CUDA, "reading the step scalars failed");
     r->minDtCourant   = h64.minDtCourant;
-    r->minDtRho       = a->p.Krho / std::fabs(h64.maxDivv);
+    r->minDtRho       = h64.maxDivv == -INFINITY ? double(INFINITY) : a->p.Krho / std::fabs(h64.maxDivv);
     r->totalNeighbors = h.totalNeighbors;
     r->maxNc          = h.maxNc;
     r->numHIterated   = h.numHIterated;
