@@ -88,7 +88,9 @@ struct SearchShared
     float          quadBox[6 * kTileQuads];
     int            leafKey[C::kMaxLeaves];   // leaf index (sort key), later: particle count of the sorted leaf
     unsigned short leafTile[C::kMaxLeaves];  // offset of the leaf's particles in its tile
-    unsigned short quadMeta[kTileQuads];  // provisional word of the quad << 3 | position in the word
+    // provisional word of the quad << 5 | bit position of the quad's nibble in the word's hit mask (28 - 4 quad)
+    using QuadMeta = std::conditional_t<(C::kMaxWords * 32 > 65536), unsigned, unsigned short>;
+    QuadMeta       quadMeta[kTileQuads];
     unsigned       keep[kSearchWarps][kKeepWords]; // per warp: quads of the tile within reach of its targets
     // (everything above is dead once the pair tests are done: the list decode stages the hit-mask columns there)
     unsigned       usedBits[C::kMaxWords];   // union over the block's targets of the hit masks, per provisional word
@@ -108,6 +110,7 @@ struct SearchShared
     int            maxLeafCount; // most particles in one of the block's leaves
     int            scan[kSearchWarps];
     int            selfP[kSearchThreads]; // provisional slot of each target's own particle
+    double         origin[3];             // block origin (registers are short in the quad walk: reloaded where needed)
     unsigned       candBegin, numCand, nextBlock;
 };
 
@@ -132,10 +135,75 @@ struct SearchArgs
 template<class C>
 constexpr size_t searchSharedBytes() { return sizeof(SearchShared<C>); }
 
+//! load that the compiler neither hoists nor merges with an earlier one (values needed on rare paths only are
+//! re-read there instead of occupying registers across the quad walk)
+__device__ __forceinline__ double reload(const double* p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+/* Shared-memory accesses of the quad walk through an explicit 32-bit shared-space address. Left to itself, ptxas
+ * re-derives the shared window base (S2R SR_CgaCtaId, MOV, LEA) at the top of every quad iteration; the base obtained
+ * once through a volatile cvta cannot be rematerialised and stays in a register. */
+#ifndef SPHX_SEARCH_SADDR
+#define SPHX_SEARCH_SADDR 1
+#endif
+__device__ __forceinline__ unsigned sharedBase(const void* p)
+{
+    unsigned r;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldsF4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned ldsU16(unsigned addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned ldsU32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 ldsU32x2(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+//! index of the most significant set bit (x != 0)
+__device__ __forceinline__ unsigned highestBit(unsigned x)
+{
+    unsigned p;
+    asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(x));
+    return p;
+}
+__device__ __forceinline__ void redOrShared(unsigned addr, unsigned v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 //! the reference's pair predicate (findneighbors.hpp:33-60,117,134), every fp64 operation rounded separately
-__device__ __noinline__ bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
-                                       const double* __restrict__ z, unsigned j, double xi, double yi, double zi,
-                                       bool usePbc, const DevBox& box, float radiusSq)
+#ifndef SPHX_EXACT_INLINE
+#define SPHX_EXACT_INLINE 1 // 1: one inlined copy of the exact predicate in the quad loop instead of a call
+#endif
+#if SPHX_EXACT_INLINE
+#define SPHX_EXACT_ATTR __forceinline__
+#else
+#define SPHX_EXACT_ATTR __noinline__
+#endif
+__device__ SPHX_EXACT_ATTR bool exactPair(const double* __restrict__ x, const double* __restrict__ y,
+                                          const double* __restrict__ z, unsigned j, double xi, double yi, double zi,
+                                          bool usePbc, const DevBox& box, float radiusSq)
 {
     double dx = __dsub_rn(x[j], xi);
     double dy = __dsub_rn(y[j], yi);
@@ -196,12 +264,14 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
     constexpr int T    = kBlockTargets;
     const int     t    = threadIdx.x;
     const int     lane = t & 31, warp = t >> 5;
+#if SPHX_SEARCH_SADDR
+    const unsigned sb = sharedBase(&s);
+#endif
 
     const unsigned iBlock0 = a.first + blk * T;
     const unsigned i       = iBlock0 + t;
     const bool     valid   = i < a.last;
     const unsigned il      = valid ? i : a.last - 1;
-    const double   xi = a.x[il], yi = a.y[il], zi = a.z[il];
     float          hi        = a.h[il];
     bool           hChanged  = false;
     int            iteration = 0;
@@ -210,7 +280,6 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
     const unsigned ngmax     = a.ngmax;
     const DevBox&  box       = a.box;
 
-    double ox = 0, oy = 0, oz = 0;
     bool   foldMode = false;
     int    L = 0;
     // Fallback for blocks whose targets are NOT compact in space (the SFC leaves the particle distribution and
@@ -226,7 +295,9 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
     for (;;)
     {
         // ---------------------------------------------------------------------------------------------------------
-        // per-target search parameters (findneighbors.hpp:93-100)
+        // per-target search parameters (findneighbors.hpp:93-100). The fp64 position is needed up to the fp32 filter
+        // set-up only (and by the rare exact decisions, which re-read it): not kept in registers across the quad walk
+        const double xi = reload(a.x + il), yi = reload(a.y + il), zi = reload(a.z + il);
         const float  radiusSq = __fmul_rn(__fmul_rn(4.0f, hi), hi);
         const double ext      = __dmul_rn(2.0, double(hi));
         const bool   inside   = __dsub_rn(xi, ext) >= box.xmin && __dsub_rn(yi, ext) >= box.ymin &&
@@ -278,7 +349,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
         const double bcx = 0.5 * (up[0] + lo[0]), bsx = 0.5 * (up[0] - lo[0]);
         const double bcy = 0.5 * (up[1] + lo[1]), bsy = 0.5 * (up[1] - lo[1]);
         const double bcz = 0.5 * (up[2] + lo[2]), bsz = 0.5 * (up[2] - lo[2]);
-        ox = bcx, oy = bcy, oz = bcz;
+        if (t == 0) s.origin[0] = bcx, s.origin[1] = bcy, s.origin[2] = bcz; // read after the barriers of the walk
         if (precise)
         {
             const float rr = float(r) * 1.0001f;
@@ -541,7 +612,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
         // ---------------------------------------------------------------------------------------------------------
         // fp32 filter thresholds. |d2_fp32 - d2_exact| <= 2^-24 (7 r E + 6.5 r^2) near the decision boundary
         // (E bounds every relative coordinate); pairs inside the margin are decided by the exact predicate.
-        const float  tx = float(xi - ox), ty = float(yi - oy), tz = float(zi - oz);
+        const float  tx = float(xi - s.origin[0]), ty = float(yi - s.origin[1]), tz = float(zi - s.origin[2]);
         const float2 ntx = make_float2(-tx, -tx), nty = make_float2(-ty, -ty), ntz = make_float2(-tz, -tz);
         float        r2lo, r2hi;
         {
@@ -576,7 +647,8 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
 
             // stage the particles and the boxes of their quads (a quad = four lanes; padding does not count)
             {
-                int l = lb;
+                const double ox = s.origin[0], oy = s.origin[1], oz = s.origin[2];
+                int          l = lb;
                 for (int p0 = 0; p0 < tileN; p0 += T)
                 {
                     const int  p  = p0 + t;
@@ -589,7 +661,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                         while (p >= s.leafTile[l] + ((s.leafKey[l] + 3) & ~3))
                             ++l;
                         const int off = p - s.leafTile[l]; // negative below the first leaf of the tile: padding
-                        meta = ((unsigned(s.leafW0[l]) + unsigned(max(off, 0) >> 5)) << 3) | (unsigned(off >> 2) & 7u);
+                        meta = ((unsigned(s.leafW0[l]) + unsigned(max(off, 0) >> 5)) << 5) | (28u - 4u * (unsigned(off >> 2) & 7u));
                         if (off >= 0 && off < s.leafKey[l])
                         {
                             const unsigned j = unsigned(s.leafFirst[l] + off);
@@ -618,7 +690,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                             s.quadBox[d * kTileQuads + Q]       = qlo[d];
                             s.quadBox[(3 + d) * kTileQuads + Q] = qhi[d];
                         }
-                        s.quadMeta[Q] = (unsigned short)meta;
+                        s.quadMeta[Q] = typename Shared::QuadMeta(meta);
                     }
                 }
             }
@@ -660,7 +732,11 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                 {
                     if (curW == selfW) mask &= selfClear; // the target itself is not a neighbour
                     const unsigned any = __reduce_or_sync(kFullMask, mask);
+#if SPHX_SEARCH_SADDR
+                    if (any && lane == 0) redOrShared(sb + unsigned(offsetof(Shared, usedBits)) + 4u * unsigned(curW), any);
+#else
                     if (any && lane == 0) atomicOr(&s.usedBits[curW], any);
+#endif
                     if (mask)
                     {
                         count += __popc(mask);
@@ -676,20 +752,40 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                 const int     nKw  = ((tileN >> 2) + 31) >> 5;
                 for (int kw = 0; kw < nKw; ++kw)
                 {
+#if SPHX_SEARCH_SADDR
+                    unsigned bits = ldsU32(sb + unsigned(offsetof(Shared, keep)) + 4u * unsigned(warp * kKeepWords + kw));
+#else
                     unsigned bits = s.keep[warp][kw];
+#endif
                     while (bits)
                     {
                         const int Q = kw * 32 + __ffs(bits) - 1;
                         bits &= bits - 1;
+#if SPHX_SEARCH_SADDR
+                        const unsigned meta =
+                            sizeof(typename Shared::QuadMeta) == 2
+                                ? ldsU16(sb + unsigned(offsetof(Shared, quadMeta)) + 2u * unsigned(Q))
+                                : ldsU32(sb + unsigned(offsetof(Shared, quadMeta)) + 4u * unsigned(Q));
+#else
                         const unsigned meta = s.quadMeta[Q];
-                        const int      w = int(meta >> 3), q = int(meta & 7u);
+#endif
+                        const int      w = int(meta >> 5);
+                        const unsigned sh = meta & 31u; // the quad's four slots are bits sh + 3 .. sh of the hit mask
+#if SPHX_SEARCH_SADDR
+                        // (issued before the word check: the loads do not wait for the meta entry and the flush)
+                        const unsigned qa = sb + unsigned(offsetof(Shared, tileX)) + 16u * unsigned(Q);
+                        const float4   X = ldsF4(qa), Y = ldsF4(qa + unsigned(sizeof(s.tileX))),
+                                     Z = ldsF4(qa + 2u * unsigned(sizeof(s.tileX)));
+#endif
                         if (w != curW)
                         {
                             if (curW >= 0) flush();
                             curW = w, mask = 0;
                         }
                         // distances of one quad in packed f32x2 arithmetic
+#if !SPHX_SEARCH_SADDR
                         const float4 X = px[Q], Y = py[Q], Z = pz[Q];
+#endif
                         const float2 dx0 = __fadd2_rn(make_float2(X.x, X.y), ntx), dx1 = __fadd2_rn(make_float2(X.z, X.w), ntx);
                         const float2 dy0 = __fadd2_rn(make_float2(Y.x, Y.y), nty), dy1 = __fadd2_rn(make_float2(Y.z, Y.w), nty);
                         const float2 dz0 = __fadd2_rn(make_float2(Z.x, Z.y), ntz), dz1 = __fadd2_rn(make_float2(Z.z, Z.w), ntz);
@@ -707,7 +803,26 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                             const float d2[4] = {s0.x, s0.y, s1.x, s1.y};
                             const int   l     = s.wordLeaf[w];
                             const int   n     = s.leafKey[l];
-                            const int   off0  = 32 * (w - int(s.leafW0[l])) + 4 * q;
+                            const int   off0  = 32 * (w - int(s.leafW0[l])) + int(28u - sh);
+#if SPHX_EXACT_INLINE
+                            // one copy of the fp64 code, the four pairs rotate through g0 / f0
+                            unsigned g0 = eb[0], g1 = eb[1], g2 = eb[2], g3 = eb[3];
+                            float    f0 = d2[0], f1 = d2[1], f2 = d2[2], f3 = d2[3];
+#pragma unroll 1
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                bool h = g0 >> 31;
+                                if (!h && f0 < r2hi)
+                                {
+                                    const int off = off0 + u;
+                                    h = unsigned(off) < unsigned(n) && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), reload(a.x + il),
+                                                             reload(a.y + il), reload(a.z + il), usePbc, box, radiusSq);
+                                }
+                                nib = (nib << 1) | unsigned(h);
+                                g0 = g1, g1 = g2, g2 = g3;
+                                f0 = f1, f1 = f2, f2 = f3;
+                            }
+#else
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                             {
@@ -715,11 +830,12 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                                 if (!h && d2[u] < r2hi)
                                 {
                                     const int off = off0 + u;
-                                    h = unsigned(off) < unsigned(n) && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), xi, yi, zi,
-                                                             usePbc, box, radiusSq);
+                                    h = unsigned(off) < unsigned(n) && exactPair(a.x, a.y, a.z, unsigned(s.leafFirst[l] + off), reload(a.x + il),
+                                                             reload(a.y + il), reload(a.z + il), usePbc, box, radiusSq);
                                 }
                                 nib = (nib << 1) | unsigned(h);
                             }
+#endif
                         }
                         else
                         {
@@ -727,7 +843,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                             for (int u = 0; u < 4; ++u)
                                 nib = __funnelshift_l(eb[u], nib, 1); // (nib << 1) | sign(e)
                         }
-                        mask |= nib << (28 - 4 * q);
+                        mask |= nib << sh;
                     }
                 }
                 if (curW >= 0) flush();
@@ -756,6 +872,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
     // -------------------------------------------------------------------------------------------------------------
     const unsigned ncSph = 1 + count;
     BlockDesc      desc;
+    const double ox = s.origin[0], oy = s.origin[1], oz = s.origin[2];
     desc.ox = ox, desc.oy = oy, desc.oz = oz;
     desc.flags = foldMode ? kBlockFold : 0u;
     // diagnostics (sim.py: block_stats): leaves in reach, tiles, precise walk, search repetitions of the h-iteration
@@ -847,6 +964,21 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                 unsigned       q    = 0, mask = 0, ub = 0, pre = 0;
                 while (k < kc)
                 {
+#if SPHX_SEARCH_SADDR
+                    if (mask == 0)
+                    {
+                        if (q == nb) break;
+                        const uint2 en = ldsU32x2(stgAddr + q * unsigned(T * sizeof(uint2)));
+                        ++q;
+                        mask = en.x;
+                        ub   = ldsU32(sb + unsigned(offsetof(Shared, usedBits)) + 4u * en.y);
+                        // (minus one: the hit itself is a used slot, it is counted by popc(ub >> p) below)
+                        pre  = ldsU16(sb + unsigned(offsetof(Shared, wordPrefix)) + 2u * en.y) - 1u;
+                    }
+                    const unsigned p = highestBit(mask); // slot 31 - p of the word
+                    mask ^= 1u << p;
+                    const unsigned e = pre + __popc(ub >> p); // used slots before this one
+#else
                     if (mask == 0)
                     {
                         if (q == nb) break;
@@ -858,6 +990,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                     const unsigned b = __clz(mask);
                     mask &= ~(0x80000000u >> b);
                     const unsigned e = pre + __popc(ub & ~(0xffffffffu >> b));
+#endif
                     v0 = __funnelshift_r(v0, v1, 16), v1 = __funnelshift_r(v1, v2, 16), v2 = __funnelshift_r(v2, v3, 16);
                     v3 = __funnelshift_r(v3, e, 16);
                     ++k;
