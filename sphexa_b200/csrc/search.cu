@@ -73,6 +73,13 @@ constexpr int      kLeafClasses = SPHX_LEAF_CLASSES; // leaf interleave of the t
 #define SPHX_DECODE_BATCH 16
 #endif
 constexpr unsigned kDecodeBatch = SPHX_DECODE_BATCH; // list decode: hit-mask entries per lane staged in shared memory at a time
+#ifndef SPHX_QUAD_UNROLL
+#define SPHX_QUAD_UNROLL 1 // quad walk / list decode: 2 = two iterations per taken back-edge (measured: 1 % slower)
+#endif
+#ifndef SPHX_DECODE_UNROLL
+#define SPHX_DECODE_UNROLL 1
+#endif
+constexpr int kQuadUnroll = SPHX_QUAD_UNROLL, kDecodeUnroll = SPHX_DECODE_UNROLL;
 constexpr int kTileQuads      = kTileCap / 4;
 constexpr int kKeepWords      = kTileQuads / 32;
 static_assert(kTileQuads % 32 == 0, "quad cull: whole ballots per tile");
@@ -757,6 +764,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
 #else
                     unsigned bits = s.keep[warp][kw];
 #endif
+#pragma unroll kQuadUnroll
                     while (bits)
                     {
                         const int Q = kw * 32 + __ffs(bits) - 1;
@@ -962,6 +970,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 const unsigned nb   = numEnt > r0 ? min(kDecodeBatch, numEnt - r0) : 0u;
                 unsigned       q    = 0, mask = 0, ub = 0, pre = 0;
+#pragma unroll kDecodeUnroll
                 while (k < kc)
                 {
 #if SPHX_SEARCH_SADDR
@@ -1077,7 +1086,7 @@ __device__ __forceinline__ void searchBlock(const SearchArgs& a, SearchShared<C>
 //! persistent CTAs take blocks of 128 targets from a work counter; each CTA owns one slice of the hit-mask scratch.
 //! The big instantiation takes its blocks from the overflow list the standard one left behind.
 #ifndef SPHX_SEARCH_CTAS
-#define SPHX_SEARCH_CTAS 7 // resident CTAs per SM the register allocation aims for
+#define SPHX_SEARCH_CTAS 8 // resident CTAs per SM the register allocation aims for (8: 64 registers; 7: 72, 5 % slower)
 #endif
 template<bool IterateH, class C>
 __global__ void __launch_bounds__(kSearchThreads, C::kOwnScratch ? 1 : SPHX_SEARCH_CTAS)

@@ -35,7 +35,10 @@ constexpr unsigned kMaxNgmaxStep   = 384; // list vectors per target: (ngmax + 8
 //! hit-mask entries {mask, word} per target of the block search: every entry holds at least one neighbour, so ngmax + 1
 //! entries hold any list that does not overflow ngmax (multiple of 4: the columns of a CTA stay 16-byte aligned)
 __host__ __device__ inline unsigned maskRowsOf(unsigned ngmax) { return (ngmax + 4u) & ~3u; }
-constexpr unsigned kSearchMaxCtas  = 1024; // resident CTAs of the persistent block search (each owns a scratch slice)
+#ifndef SPHX_SEARCH_MAX_CTAS
+#define SPHX_SEARCH_MAX_CTAS 1280 // >= resident CTAs per SM x SMs (B200: 8 x 148 = 1184)
+#endif
+constexpr unsigned kSearchMaxCtas  = SPHX_SEARCH_MAX_CTAS; // resident CTAs of the persistent block search (each owns a scratch slice)
 constexpr int      kSearchWork     = 5;   // StepScalars::work slot of the block search (0..4: the loop kernels)
 
 constexpr unsigned kBlockFold = 1u; // BlockDesc::flags: fold mode
