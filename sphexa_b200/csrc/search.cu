@@ -8,7 +8,7 @@
  *   sph::findNeighborsSph            sph/include/sph/find_neighbors.hpp:11-44        (h-iteration)
  *   cstone::traverseNeighbors        domain/include/cstone/traversal/find_neighbors.cuh:182-489 (not followed)
  *
- * A CTA owns 128 SFC-consecutive targets at a time (one per thread, persistent CTAs, seven per SM).
+ * A CTA owns 128 SFC-consecutive targets at a time (one per thread, persistent CTAs, eight per SM).
  *  1. bounding box of the targets' 2h-spheres; level-synchronous walk of the octree by all 128 threads collects the
  *     leaves that overlap it; the leaves are ranked by leaf index (deterministic) and stored interleaved (ranks = g
  *     mod 8 together), so that a tile samples the whole candidate region and the warps' work per tile is balanced.
@@ -43,7 +43,7 @@ constexpr int kSearchWarps   = kSearchThreads / 32;
 #define SPHX_TILE_CAP 768
 #endif
 constexpr int kTileCap       = SPHX_TILE_CAP; // staged particles per tile (incl. padding), multiple of 128
-/*! Per-block table sizes. The standard set fits seven CTAs per SM. A block whose reach holds more leaves (cavities and
+/*! Per-block table sizes. The standard set fits eight CTAs per SM. A block whose reach holds more leaves (cavities and
  *  shells of an evolved blast wave: large search spheres next to finely resolved regions) is pushed on an overflow list
  *  and redone by the same code instantiated with the big set, one CTA per SM, with scratch arrays of its own instead of
  *  the aliased ones. */
